@@ -1,0 +1,250 @@
+// llc_device.cu -- device-level C ABI (include/aocl_llc_gpu.h): context, workspace and the
+// kernel launch sequences for RAP compress / decompress and batched pages.
+#include "llc_kernels.cuh"
+#include "../../include/aocl_llc_gpu.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+using namespace llc;
+
+static std::atomic<uint64_t> g_launches{0};
+#define LLC_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+    do {                                                              \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);   \
+        g_launches.fetch_add(1, std::memory_order_relaxed);           \
+    } while (0)
+
+struct aocl_gpu_ctx_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    uint8_t* ws = nullptr;          // growable HBM workspace (scratch slots, tables, plans)
+    size_t ws_bytes = 0;
+    CallResult* d_res = nullptr;    // result block on the device
+    CallResult* h_res = nullptr;    // pinned mirror
+    int decode_blocks = 0;          // persistent grid size of decode_parts_kernel
+    bool lz4_frameless = false;
+    bool batch_mode = false;        // last enqueue was a batch call (finish() returns -failures)
+    int last_rc = 0;                // enqueue-time failure to report from finish()
+};
+
+static bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    if (getenv("AOCL_GPU_VERBOSE")) fprintf(stderr, "[aocl-llc-b200] %s: %s\n", what, cudaGetErrorString(e));
+    return false;
+}
+
+static bool ensure_ws(aocl_gpu_ctx_t c, size_t bytes) {
+    if (bytes <= c->ws_bytes) return true;
+    if (c->ws) { cudaStreamSynchronize(c->stream); cudaFree(c->ws); c->ws = nullptr; c->ws_bytes = 0; }
+    bytes = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    if (!cuda_ok(cudaMalloc(&c->ws, bytes), "cudaMalloc(workspace)")) return false;
+    c->ws_bytes = bytes;
+    return true;
+}
+
+extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* stream) {
+    if (!out) return -5;
+    *out = nullptr;
+    int count = 0;
+    if (!cuda_ok(cudaGetDeviceCount(&count), "cudaGetDeviceCount") || count == 0) return -2;
+    if (device < 0 && !cuda_ok(cudaGetDevice(&device), "cudaGetDevice")) return -2;
+    if (device >= count || !cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return -2;
+    aocl_gpu_ctx_t c = new aocl_gpu_ctx_s();
+    c->device = device;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (stream) c->stream = (cudaStream_t)stream;
+    else { if (!cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return -2; } c->own_stream = true; }
+    if (!cuda_ok(cudaMalloc(&c->d_res, sizeof(CallResult)), "cudaMalloc(result)") ||
+        !cuda_ok(cudaMallocHost(&c->h_res, sizeof(CallResult)), "cudaMallocHost(result)")) { aocl_gpu_ctx_destroy(c); return -2; }
+    memset(c->h_res, 0, sizeof(CallResult));
+    // opt in to the shared-memory sizes the encoders need (16 KiB LZ4 table, 32 KiB Snappy table)
+    cudaFuncSetAttribute(lz4_encode_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
+    cudaFuncSetAttribute(lz4_encode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
+    cudaFuncSetAttribute(snappy_encode_frags_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+    cudaFuncSetAttribute(encode_pages_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_parts_kernel, 128, 0);
+    if (per_sm < 1) per_sm = 1;
+    c->decode_blocks = per_sm * c->sm_count;
+    *out = c;
+    return 0;
+}
+
+extern "C" void aocl_gpu_ctx_destroy(aocl_gpu_ctx_t c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->ws) cudaFree(c->ws);
+    if (c->d_res) cudaFree(c->d_res);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" void* aocl_gpu_ctx_stream(aocl_gpu_ctx_t c) { return c ? (void*)c->stream : nullptr; }
+extern "C" void aocl_gpu_set_lz4_frameless(aocl_gpu_ctx_t c, int32_t on) { if (c) c->lz4_frameless = on != 0; }
+extern "C" uint64_t aocl_gpu_launch_count(void) { return g_launches.load(); }
+
+extern "C" int32_t aocl_gpu_partition_count(int32_t codec, size_t n) {
+    return (int32_t)partition_count(n, codec == AOCL_GPU_LZ4 ? kLz4Window : kSnappyBlock);
+}
+extern "C" size_t aocl_gpu_compress_bound(int32_t codec, size_t n) {
+    const size_t T = (size_t)aocl_gpu_partition_count(codec, n);
+    const size_t frame = T > 1 ? 16 + 12 * T : 0;
+    if (codec == AOCL_GPU_LZ4) return frame + n + n / 255 + 16 + 8 * T;   // stitching can lengthen one header per partition
+    return frame + 32 + n + n / 6;
+}
+
+static void begin_call(aocl_gpu_ctx_t c) {
+    cudaSetDevice(c->device);
+    cudaMemsetAsync(c->d_res, 0, sizeof(CallResult), c->stream);
+    c->batch_mode = false;
+    c->last_rc = 0;
+}
+static void end_call(aocl_gpu_ctx_t c) {
+    cudaMemcpyAsync(c->h_res, c->d_res, sizeof(CallResult), cudaMemcpyDeviceToHost, c->stream);
+}
+
+extern "C" int64_t aocl_gpu_finish(aocl_gpu_ctx_t c) {
+    if (!c) return -5;
+    if (c->last_rc) return c->last_rc;
+    if (!cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize")) return -2;
+    if (!cuda_ok(cudaGetLastError(), "kernel")) return -2;
+    if (c->batch_mode) return -(int64_t)c->h_res->error;
+    if (c->h_res->error) return -2;
+    return c->h_res->value;
+}
+
+// ---------------------------------------------------------------------------------- decompress
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, size_t n,
+                                                   void* d_out, size_t out_cap, uint32_t first, uint32_t count,
+                                                   uint64_t out_origin) {
+    if (!c) return -5;
+    begin_call(c);
+    if ((codec != AOCL_GPU_LZ4 && codec != AOCL_GPU_SNAPPY) || !d_in || n == 0 || n > 0xffffffffull || (!d_out && out_cap)) {
+        c->last_rc = -2; return -2;
+    }
+    if (!ensure_ws(c, sizeof(PartDesc) * kMaxPartitions)) { c->last_rc = -2; return -2; }
+    PartDesc* parts = reinterpret_cast<PartDesc*>(c->ws);
+    const bool ranged = !(first == 0 && count == 0xffffffffu);
+    // for a range the capacity check applies to the range, not to the whole stream
+    LLC_LAUNCH(rap_parse_kernel, 1, 1024, 0, c->stream, codec, (const uint8_t*)d_in, (uint64_t)n,
+               ranged ? ~0ull : (uint64_t)out_cap, parts, c->d_res);
+    LLC_LAUNCH(decode_parts_kernel, c->decode_blocks, 128, 0, c->stream, codec, (const uint8_t*)d_in, (uint8_t*)d_out,
+               parts, c->d_res, first, count, out_origin);
+    if (ranged) LLC_LAUNCH(range_total_kernel, 1, 256, 0, c->stream, parts, c->d_res, first, count);
+    end_call(c);
+    return 0;
+}
+
+extern "C" int32_t aocl_gpu_decompress_async(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, size_t n, void* d_out,
+                                             size_t out_cap) {
+    return aocl_gpu_decompress_range_async(c, codec, d_in, n, d_out, out_cap, 0, 0xffffffffu, 0);
+}
+
+extern "C" int64_t aocl_gpu_decompress(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, size_t n, void* d_out, size_t out_cap) {
+    aocl_gpu_decompress_async(c, codec, d_in, n, d_out, out_cap);
+    return aocl_gpu_finish(c);
+}
+
+// ---------------------------------------------------------------------------------- compress
+extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, size_t n, void* d_out,
+                                           size_t out_cap) {
+    if (!c) return -5;
+    begin_call(c);
+    if ((codec != AOCL_GPU_LZ4 && codec != AOCL_GPU_SNAPPY) || (!d_in && n) || !d_out || out_cap == 0 || n > 0x7E000000ull) {
+        c->last_rc = -2; return -2;
+    }
+    const uint8_t* src = (const uint8_t*)d_in;
+    uint8_t* dst = (uint8_t*)d_out;
+    if (codec == AOCL_GPU_LZ4) {
+        const uint32_t T = c->lz4_frameless ? 1u : partition_count(n, kLz4Window);
+        if (T == 1) {                                          // frame-less block, lz4.c:2674-2677 / 2485-2541
+            const uint64_t bound = n + n / 255 + 16;
+            LLC_LAUNCH(lz4_encode_single_kernel, 1, 32, 16384, c->stream, src, (uint32_t)n, dst,
+                       out_cap >= bound ? -1ll : (long long)out_cap, c->d_res);
+        } else {
+            const uint64_t pmax = n / T + n % T;
+            const uint64_t slot = align_up(pmax + pmax / 255 + 32, 256);
+            const size_t o_rec = 0, o_plan = align_up(o_rec + sizeof(Lz4Rec) * T, 256);
+            const size_t o_scr = align_up(o_plan + sizeof(Lz4Plan) * T, 256);
+            if (!ensure_ws(c, o_scr + slot * T)) { c->last_rc = -2; return -2; }
+            Lz4Rec* rec = reinterpret_cast<Lz4Rec*>(c->ws + o_rec);
+            Lz4Plan* plan = reinterpret_cast<Lz4Plan*>(c->ws + o_plan);
+            uint8_t* scratch = c->ws + o_scr;
+            LLC_LAUNCH(lz4_encode_parts_kernel, T, 32, 16384, c->stream, src, (uint64_t)n, T, scratch, slot, rec);
+            LLC_LAUNCH(lz4_stitch_plan_kernel, 1, 1024, 0, c->stream, scratch, slot, rec, (uint64_t)n, T, dst,
+                       (uint64_t)out_cap, plan, c->d_res);
+            LLC_LAUNCH(lz4_compact_kernel, T, 256, 0, c->stream, src, scratch, slot, rec, plan, dst, c->d_res);
+        }
+    } else {
+        if (out_cap < 32 + n + n / 6) { c->last_rc = -2; return -2; }   // api/codec.cpp:262-265
+        const uint32_t T = partition_count(n, kSnappyBlock);
+        const SnappyGeom g = snappy_geom(n, T);
+        const uint32_t F = g.frags_total;
+        const uint64_t slot = 76544;                           // >= 32 + 65536 + 65536/6, multiple of 256
+        const size_t o_len = 0, o_off = align_up(o_len + sizeof(uint32_t) * (F + 1), 256);
+        const size_t o_scr = align_up(o_off + sizeof(uint64_t) * (F + 1), 256);
+        if (!ensure_ws(c, o_scr + slot * (F + 1))) { c->last_rc = -2; return -2; }
+        uint32_t* frag_len = reinterpret_cast<uint32_t*>(c->ws + o_len);
+        uint64_t* frag_off = reinterpret_cast<uint64_t*>(c->ws + o_off);
+        uint8_t* scratch = c->ws + o_scr;
+        if (F) LLC_LAUNCH(snappy_encode_frags_kernel, F, 32, 32768, c->stream, src, g, scratch, slot, frag_len);
+        LLC_LAUNCH(snappy_plan_kernel, 1, 1024, 0, c->stream, g, frag_len, frag_off, dst, (uint64_t)out_cap, c->d_res);
+        if (F) LLC_LAUNCH(snappy_compact_kernel, F, 256, 0, c->stream, scratch, slot, frag_len, frag_off, dst, c->d_res);
+    }
+    end_call(c);
+    return 0;
+}
+
+extern "C" int64_t aocl_gpu_compress(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, size_t n, void* d_out, size_t out_cap) {
+    aocl_gpu_compress_async(c, codec, d_in, n, d_out, out_cap);
+    return aocl_gpu_finish(c);
+}
+
+// ---------------------------------------------------------------------------------- pages
+extern "C" int32_t aocl_gpu_decompress_batch_async(aocl_gpu_ctx_t c, int32_t codec, const void* const* d_in_ptrs,
+                                                   const uint32_t* d_in_sizes, void* const* d_out_ptrs,
+                                                   const uint32_t* d_out_caps, int64_t* d_status, size_t count) {
+    if (!c) return -5;
+    begin_call(c);
+    c->batch_mode = true;
+    if ((codec != AOCL_GPU_LZ4 && codec != AOCL_GPU_SNAPPY) || (count && (!d_in_ptrs || !d_in_sizes || !d_out_ptrs || !d_out_caps || !d_status))) {
+        c->last_rc = -2; return -2;
+    }
+    if (count) {
+        const uint64_t blocks = (count + 3) / 4;
+        const int grid = (int)(blocks < (uint64_t)c->decode_blocks * 4 ? blocks : (uint64_t)c->decode_blocks * 4);
+        LLC_LAUNCH(decode_pages_kernel, grid, 128, 0, c->stream, codec, (const uint8_t* const*)d_in_ptrs, d_in_sizes,
+                   (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status, (uint64_t)count, c->d_res);
+    }
+    end_call(c);
+    return 0;
+}
+
+extern "C" int32_t aocl_gpu_compress_batch_async(aocl_gpu_ctx_t c, int32_t codec, const void* const* d_in_ptrs,
+                                                 const uint32_t* d_in_sizes, void* const* d_out_ptrs,
+                                                 const uint32_t* d_out_caps, int64_t* d_status, size_t count) {
+    if (!c) return -5;
+    begin_call(c);
+    c->batch_mode = true;
+    if ((codec != AOCL_GPU_LZ4 && codec != AOCL_GPU_SNAPPY) || (count && (!d_in_ptrs || !d_in_sizes || !d_out_ptrs || !d_out_caps || !d_status))) {
+        c->last_rc = -2; return -2;
+    }
+    if (count) {
+        const size_t smem = codec == AOCL_GPU_LZ4 ? 16384 : 32768;
+        const uint64_t max_grid = (uint64_t)c->sm_count * (codec == AOCL_GPU_LZ4 ? 14 : 7) * 4;
+        const int grid = (int)(count < max_grid ? count : max_grid);
+        LLC_LAUNCH(encode_pages_kernel, grid, 32, smem, c->stream, codec, (const uint8_t* const*)d_in_ptrs, d_in_sizes,
+                   (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status, (uint64_t)count, c->d_res);
+    }
+    end_call(c);
+    return 0;
+}

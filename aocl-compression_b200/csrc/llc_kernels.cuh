@@ -1,0 +1,503 @@
+// llc_kernels.cuh -- __global__ kernels of the RAP path: frame parse/scan, per-partition
+// codec kernels, stitch/plan and compaction.  Launch logic lives in llc_device.cu.
+#pragma once
+#include "llc_common.cuh"
+#include "lz4_codec.cuh"
+#include "snappy_codec.cuh"
+
+namespace llc {
+
+// ------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one uint64 per thread (blockDim.x <= 1024, multiple of 32)
+// ------------------------------------------------------------------------------------------
+__device__ inline uint64_t block_excl_scan(uint64_t v, uint64_t* total, uint64_t* smem /* >= 33 entries */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint64_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t t = __shfl_up_sync(kFull, x, d);
+        if (lane >= d) x += t;
+    }
+    if (lane == 31) smem[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t w = lane < nwarp ? smem[lane] : 0;
+        uint64_t y = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t t = __shfl_up_sync(kFull, y, d);
+            if (lane >= d) y += t;
+        }
+        smem[lane] = y - w;                 // exclusive warp offsets
+        if (lane == 31) smem[32] = y;       // grand total
+    }
+    __syncthreads();
+    const uint64_t r = smem[warp] + x - v;
+    if (total) *total = smem[32];
+    __syncthreads();
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Decompress step 1: parse the RAP frame (or recognise a frame-less stream), validate the
+// entries and lay the partitions out in the output (exclusive scan of decomp_len).
+// Replaces aocl_setup_parallel_decompress_mt / aocl_do_partition_decompress_mt
+// (threads/threads.c:174-293) and the serial concatenation epilogues (lz4.c:4863-4881,
+// snappy.cc:2351-2366): partitions are decoded straight to their final offsets.
+// One CTA of 1024 threads.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) rap_parse_kernel(int codec, const uint8_t* __restrict__ in, uint64_t n,
+                                                         uint64_t out_cap, PartDesc* parts, CallResult* res) {
+    __shared__ uint64_t sm[40];
+    __shared__ uint32_t s_T, s_frame, s_bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_bad = 0;
+        uint32_t T = 1, frame = 0;
+        if (n >= 8 && ld_u64_bytes(in) == kRapMagic) {        // threads/threads.c:194-201
+            if (n < 16) s_bad = 1;
+            else {
+                frame = ld_u32_bytes(in + 8);
+                T = ld_u32_bytes(in + 12);
+                if (T == 0 || T > kMaxPartitions || (uint64_t)kRapHeaderBytes + (uint64_t)kRapEntryBytes * T > n ||
+                    frame > n)
+                    s_bad = 1;                                  // threads/threads.c:208-209
+            }
+        }
+        s_T = T; s_frame = frame;
+    }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) { res->error = 1; res->value = kErrCorrupt; res->parts = 0; } return; }
+    const uint32_t T = s_T, frame = s_frame;
+
+    if (frame == 0 && T == 1) {                                 // frame-less stream: one partition
+        if (tid == 0) {
+            PartDesc d;
+            d.in_off = 0; d.in_len = (uint32_t)n; d.out_off = 0;
+            d.flags = kPartLast;
+            if (codec == 0) {
+                d.out_len = (uint32_t)min(out_cap, (uint64_t)0xffffffffu);
+                res->value = 0;
+            } else {
+                uint32_t total = 0;
+                const uint32_t vb = get_varint32(in, n, &total);
+                if (vb == 0 || total > out_cap) { res->error = 1; res->value = kErrCorrupt; res->parts = 0; return; }
+                d.in_off = vb; d.in_len = (uint32_t)(n - vb); d.out_len = total; d.flags |= kPartExact;
+                res->value = total;
+            }
+            parts[0] = d;
+            res->parts = 1;
+        }
+        return;
+    }
+    // A stream with a one-entry frame (T == 1) is handled by the same table walk.
+    const uint32_t per = (T + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(T, tid * per), hi = min(T, lo + per);
+    uint64_t local = 0;
+    bool bad = false;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint8_t* e = in + kRapHeaderBytes + (uint64_t)kRapEntryBytes * i;
+        const uint32_t off = ld_u32_bytes(e), clen = ld_u32_bytes(e + 4), dlen = ld_u32_bytes(e + 8);
+        if ((uint64_t)off + clen > n) bad = true;
+        if (clen) local += dlen;                                // zero-length partitions are skipped (threads.c:264-268)
+    }
+    uint64_t total = 0;
+    uint64_t base = block_excl_scan(local, &total, sm);
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint8_t* e = in + kRapHeaderBytes + (uint64_t)kRapEntryBytes * i;
+        PartDesc d;
+        d.in_off = ld_u32_bytes(e); d.in_len = ld_u32_bytes(e + 4); d.out_len = ld_u32_bytes(e + 8);
+        d.out_off = base;
+        d.flags = kPartExact | (i == T - 1 ? kPartLast : 0u);
+        if (d.in_len) base += d.out_len;
+        parts[i] = d;
+    }
+    if (bad) atomicOr(&s_bad, 1u);
+    __syncthreads();
+    if (tid == 0) {
+        bool fail = s_bad || total > out_cap;
+        if (codec != 0 && !fail) {                              // Snappy: varint(total) follows the frame
+            uint32_t v = 0;
+            const uint32_t vb = frame <= n ? get_varint32(in + frame, n - frame, &v) : 0;
+            if (vb == 0 || v != total) fail = true;
+        }
+        res->parts = (int)T;
+        res->value = fail ? kErrCorrupt : (long long)total;
+        if (fail) res->error = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Decompress step 2: persistent grid, one warp per partition, partitions handed out through an
+// atomic ticket so long partitions do not serialise a CTA.  Decodes partitions
+// [first, first+count) of the table and writes each at out + (out_off - origin).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) decode_parts_kernel(int codec, const uint8_t* __restrict__ in, uint8_t* out,
+                                                           const PartDesc* __restrict__ parts, CallResult* res,
+                                                           uint32_t first, uint32_t count, uint64_t origin) {
+    const int lane = lane_id();
+    if (res->error) return;
+    const uint32_t T = (uint32_t)res->parts;
+    const uint32_t end = min(T, first + min(count, T));
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = first + atomicAdd(&res->next, 1u);
+        i = __shfl_sync(kFull, i, 0);
+        if (i >= end) break;
+        const PartDesc d = parts[i];
+        if (d.in_len == 0) continue;
+        uint8_t* dst = out + (d.out_off - origin);
+        int64_t got;
+        if (codec == 0) got = lz4_decode_warp(in + d.in_off, d.in_len, dst, d.out_len, (d.flags & kPartLast) != 0, lane);
+        else            got = snappy_decode_warp(in + d.in_off, d.in_len, dst, d.out_len, lane);
+        if (lane == 0) {
+            if (got < 0 || ((d.flags & kPartExact) && (uint64_t)got != d.out_len)) atomicCAS(&res->error, 0, (int)i + 1);
+            else if (!(d.flags & kPartExact)) res->value = got;     // frame-less LZ4: size is whatever was produced
+        }
+    }
+}
+
+// Range decode needs the byte count of the range rather than of the whole stream.
+__global__ void range_total_kernel(const PartDesc* __restrict__ parts, CallResult* res, uint32_t first, uint32_t count) {
+    if (res->error) return;
+    const uint32_t T = (uint32_t)res->parts;
+    const uint32_t end = min(T, first + min(count, T));
+    unsigned long long sum = 0;
+    for (uint32_t i = first + threadIdx.x; i < end; i += blockDim.x)
+        if (parts[i].in_len) sum += parts[i].out_len;
+    for (int d = 16; d; d >>= 1) sum += __shfl_down_sync(kFull, sum, d);
+    __shared__ unsigned long long acc;
+    if (threadIdx.x == 0) acc = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicAdd(&acc, sum);
+    __syncthreads();
+    if (threadIdx.x == 0) res->value = (long long)acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched pages: one warp per independent frame-less page.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) decode_pages_kernel(int codec, const uint8_t* const* __restrict__ in_ptrs,
+                                                           const uint32_t* __restrict__ in_sizes, uint8_t* const* out_ptrs,
+                                                           const uint32_t* __restrict__ out_caps, long long* status,
+                                                           uint64_t count, CallResult* res) {
+    const int lane = lane_id();
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += warps) {
+        const uint8_t* in = in_ptrs[i];
+        const uint32_t n = in_sizes[i], cap = out_caps[i];
+        int64_t got;
+        if (codec == 0) got = lz4_decode_warp(in, n, out_ptrs[i], cap, true, lane);
+        else {
+            uint32_t total = 0;
+            const uint32_t vb = get_varint32(in, n, &total);
+            if (vb == 0 || total > cap) got = kErrCorrupt;
+            else got = snappy_decode_warp(in + vb, n - vb, out_ptrs[i], total, lane);
+        }
+        if (lane == 0) {
+            status[i] = got;
+            if (got < 0) atomicAdd(&res->error, 1);
+        }
+    }
+}
+
+// One warp per block (the hash table fills the block's dynamic shared memory).
+__global__ void __launch_bounds__(32) encode_pages_kernel(int codec, const uint8_t* const* __restrict__ in_ptrs,
+                                                          const uint32_t* __restrict__ in_sizes, uint8_t* const* out_ptrs,
+                                                          const uint32_t* __restrict__ out_caps, long long* status,
+                                                          uint64_t count, CallResult* res) {
+    extern __shared__ __align__(16) uint32_t tab_mem[];
+    const int lane = lane_id();
+    for (uint64_t i = blockIdx.x; i < count; i += gridDim.x) {
+        const uint8_t* in = in_ptrs[i];
+        const uint32_t n = in_sizes[i], cap = out_caps[i];
+        uint8_t* dst = out_ptrs[i];
+        int64_t got;
+        if (codec == 0) {
+            const uint64_t bound = (uint64_t)n + n / 255 + 16;
+            got = (cap == 0) ? 0 : lz4_encode_warp(in, n, dst, cap >= bound ? -1 : (int64_t)cap, true, nullptr, tab_mem, lane);
+            if (got == 0) got = kErrCorrupt;
+        } else if ((uint64_t)cap < 32ull + n + n / 6) {
+            got = kErrCorrupt;                                  // api/codec.cpp:262-265
+        } else {
+            uint32_t op = 0;
+            if (lane == 0) op = put_varint32(dst, n);
+            op = __shfl_sync(kFull, op, 0);
+            for (uint32_t p = 0; p < n; p += kSnappyBlock) {
+                op += snappy_encode_fragment_warp(in + p, min(kSnappyBlock, n - p), dst + op,
+                                                  reinterpret_cast<uint16_t*>(tab_mem), lane);
+                __syncwarp();
+            }
+            got = op;
+        }
+        if (lane == 0) {
+            status[i] = got;
+            if (got < 0) atomicAdd(&res->error, 1);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LZ4 compress.  Step 1: one warp per RAP partition encodes into its scratch slot.
+// Replaces the `#pragma omp parallel` region of AOCL_LZ4_compress_fast_mt (lz4.c:2684-2731).
+// ------------------------------------------------------------------------------------------
+struct Lz4Rec { uint32_t body_len; uint32_t tail_len; };
+
+__global__ void __launch_bounds__(32) lz4_encode_parts_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
+                                                              uint8_t* scratch, uint64_t slot, Lz4Rec* rec) {
+    extern __shared__ __align__(16) uint32_t tab_mem[];
+    const int lane = lane_id();
+    const uint32_t i = blockIdx.x;
+    const uint64_t common = n / T, left = n % T;             // threads/threads.c:91-97,127-135
+    const uint32_t pn = (uint32_t)(common + (i == T - 1 ? left : 0));
+    uint32_t tail = 0;
+    const uint32_t body = lz4_encode_warp(src + common * i, pn, scratch + slot * i, -1, i == T - 1, &tail, tab_mem, lane);
+    if (lane == 0) { rec[i].body_len = body; rec[i].tail_len = tail; }
+}
+
+// Frame-less block written straight to the destination (T == 1, lz4.c:2674-2677).
+__global__ void __launch_bounds__(32) lz4_encode_single_kernel(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst,
+                                                               long long cap, CallResult* res) {
+    extern __shared__ __align__(16) uint32_t tab_mem[];
+    const int lane = lane_id();
+    const uint32_t got = lz4_encode_warp(src, n, dst, cap, true, nullptr, tab_mem, lane);
+    if (lane == 0) {
+        if (got == 0) { res->error = 1; res->value = kErrCorrupt; }
+        else res->value = got;
+    }
+}
+
+// Step 2: stitch plan.  Works out, for every partition, the literal carry it inherits from its
+// predecessors (a segmented sum: an all-literal partition forwards its predecessor's carry,
+// lz4.c:2808-2822), the re-encoded first token, its final offset and length, and writes the RAP
+// frame.  Replaces the serial loop lz4.c:2736-2905.  One CTA of 1024 threads.
+struct Lz4Plan {
+    uint32_t out_off;     // absolute offset in the destination stream
+    uint32_t out_len;     // bytes this partition contributes (0 for an all-literal partition)
+    uint32_t skip;        // bytes of the scratch body replaced by the new header
+    uint32_t new_ll;      // literal length of the re-encoded first sequence
+    uint32_t carry;       // inherited literal bytes
+    uint32_t token_low;   // match-length nibble of the first token
+    uint64_t carry_src;   // source offset of the inherited literals
+};
+
+__global__ void __launch_bounds__(1024) lz4_stitch_plan_kernel(const uint8_t* __restrict__ scratch, uint64_t slot,
+                                                               const Lz4Rec* __restrict__ rec, uint64_t n, uint32_t T,
+                                                               uint8_t* dst, uint64_t out_cap, Lz4Plan* plan,
+                                                               CallResult* res) {
+    __shared__ uint64_t sm[40];
+    __shared__ uint32_t s_carry_val[1024];
+    __shared__ uint32_t s_carry_flag[1024];
+    const int tid = threadIdx.x;
+    const uint32_t per = (T + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(T, tid * per), hi = min(T, lo + per);
+    const uint64_t common = n / T, left = n % T;
+
+    // pass A: segmented inclusive sum of tails; a partition with a body starts a new segment.
+    // (value, flag) pairs combine as (f2 ? v2 : v1 + v2, f1 | f2).
+    uint32_t v = 0, f = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        const bool has_body = rec[i].body_len != 0;
+        v = has_body ? rec[i].tail_len : v + rec[i].tail_len;
+        f |= has_body ? 1u : 0u;
+    }
+    s_carry_val[tid] = v; s_carry_flag[tid] = f;
+    __syncthreads();
+    // carry entering this thread's chunk = segmented sum over all earlier chunks (serial over <= 1024
+    // chunk summaries is cheap, but do it in log steps anyway)
+    for (int d = 1; d < (int)blockDim.x; d <<= 1) {
+        uint32_t pv = 0, pf = 0;
+        if (tid >= d) { pv = s_carry_val[tid - d]; pf = s_carry_flag[tid - d]; }
+        __syncthreads();
+        if (tid >= d) {
+            if (!s_carry_flag[tid]) s_carry_val[tid] += pv;
+            s_carry_flag[tid] |= pf;
+        }
+        __syncthreads();
+    }
+    uint32_t carry = tid ? s_carry_val[tid - 1] : 0;         // inclusive result of the previous chunk
+
+    // pass B: per-partition header arithmetic and output length
+    uint64_t local = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        const Lz4Rec r = rec[i];
+        Lz4Plan p;
+        p.carry = carry;
+        const uint32_t pn = (uint32_t)(common + (i == T - 1 ? left : 0));
+        p.carry_src = common * i - carry;                     // tails are contiguous in the source
+        if (r.body_len == 0) {                                // all-literal partition
+            p.out_len = 0; p.skip = 0; p.new_ll = 0; p.token_low = 0;
+            carry += r.tail_len;
+        } else {
+            const uint8_t* b = scratch + slot * i;
+            const uint32_t tok = b[0];
+            uint32_t ll = tok >> 4, skip = 1;
+            if (ll == 15) { uint32_t x; do { x = b[skip++]; ll += x; } while (x == 255); }
+            const uint32_t nl = ll + carry;
+            const uint32_t hdr = 1 + (nl >= 15 ? (nl - 15) / 255 + 1 : 0);
+            p.skip = skip; p.new_ll = nl; p.token_low = tok & 15;
+            p.out_len = hdr + carry + (r.body_len - skip);
+            carry = r.tail_len;
+        }
+        (void)pn;
+        p.out_off = 0;
+        plan[i] = p;
+        local += p.out_len;
+    }
+    uint64_t total = 0;
+    const uint64_t frame = (uint64_t)kRapHeaderBytes + (uint64_t)kRapEntryBytes * T;
+    uint64_t base = frame + block_excl_scan(local, &total, sm);
+    total += frame;
+    const bool fits = total <= out_cap && total <= 0xffffffffull;
+
+    // pass C: offsets + RAP entries (lz4.c:2763-2780, 2879-2896)
+    carry = tid ? s_carry_val[tid - 1] : 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        const Lz4Rec r = rec[i];
+        const uint32_t pn = (uint32_t)(common + (i == T - 1 ? left : 0));
+        plan[i].out_off = (uint32_t)base;
+        const uint32_t olen = plan[i].out_len;
+        uint32_t dlen;
+        if (r.body_len == 0) { dlen = 0; carry += r.tail_len; }
+        else { dlen = pn - r.tail_len + carry; carry = r.tail_len; }
+        if (fits) {
+            uint8_t* e = dst + kRapHeaderBytes + (uint64_t)kRapEntryBytes * i;
+            st_u32_bytes(e, (uint32_t)base); st_u32_bytes(e + 4, olen); st_u32_bytes(e + 8, dlen);
+        }
+        base += olen;
+    }
+    if (tid == 0) {
+        if (fits) {
+            st_u32_bytes(dst, (uint32_t)kRapMagic); st_u32_bytes(dst + 4, (uint32_t)(kRapMagic >> 32));
+            st_u32_bytes(dst + 8, (uint32_t)frame); st_u32_bytes(dst + 12, T);    // threads/threads.c:105-110
+            res->value = (long long)total;
+        } else { res->error = 1; res->value = kErrCorrupt; }
+    }
+}
+
+// dst-aligned word copy with arbitrary source alignment (block-cooperative)
+__device__ inline void block_copy(uint8_t* dst, const uint8_t* src, uint32_t len) {
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t head = min(len, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3));
+    if (tid < head) dst[tid] = src[tid];
+    const uint32_t words = (len - head) >> 2;
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + head);
+    const uint8_t* s = src + head;
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(s);
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+    const unsigned sh = (unsigned)(sa & 3) * 8;
+    if (sh == 0) for (uint32_t i = tid; i < words; i += nt) d4[i] = s4[i];
+    else for (uint32_t i = tid; i < words; i += nt) d4[i] = __funnelshift_r(s4[i], s4[i + 1], sh);
+    const uint32_t done = head + (words << 2);
+    if (done + tid < len) dst[done + tid] = src[done + tid];
+}
+
+// Step 3: compaction.  CTA i writes [re-encoded first token][inherited literals][rest of body i]
+// at its final offset.  Replaces the memcpy chain of lz4.c:2825-2877.
+__global__ void __launch_bounds__(256) lz4_compact_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ scratch,
+                                                          uint64_t slot, const Lz4Rec* __restrict__ rec,
+                                                          const Lz4Plan* __restrict__ plan, uint8_t* dst,
+                                                          const CallResult* res) {
+    if (res->error) return;
+    const uint32_t i = blockIdx.x;
+    const Lz4Plan p = plan[i];
+    if (p.out_len == 0) return;
+    uint8_t* o = dst + p.out_off;
+    const uint32_t nl = p.new_ll;
+    const uint32_t ext = nl >= 15 ? (nl - 15) / 255 + 1 : 0;
+    if (threadIdx.x == 0) o[0] = (uint8_t)((min(nl, 15u) << 4) | p.token_low);
+    for (uint32_t j = threadIdx.x; j < ext; j += blockDim.x) o[1 + j] = (j + 1 < ext) ? (uint8_t)255 : (uint8_t)((nl - 15) % 255);
+    block_copy(o + 1 + ext, src + p.carry_src, p.carry);
+    block_copy(o + 1 + ext + p.carry, scratch + slot * i + p.skip, rec[i].body_len - p.skip);
+}
+
+// ------------------------------------------------------------------------------------------
+// Snappy compress.  Step 1: one warp per <=64 KiB fragment (the unit AOCL_CompressFragment works
+// on; snappy.cc:1762-1818 runs them back to back inside each partition).
+// ------------------------------------------------------------------------------------------
+struct SnappyGeom {
+    uint64_t n; uint32_t T; uint32_t frags_common; uint32_t frags_total; uint64_t common; uint64_t left;
+};
+__host__ __device__ inline SnappyGeom snappy_geom(uint64_t n, uint32_t T) {
+    SnappyGeom g;
+    g.n = n; g.T = T; g.common = n / T; g.left = n % T;
+    g.frags_common = (uint32_t)((g.common + kSnappyBlock - 1) / kSnappyBlock);
+    const uint32_t last = (uint32_t)((g.common + g.left + kSnappyBlock - 1) / kSnappyBlock);
+    g.frags_total = (T - 1) * g.frags_common + last;
+    return g;
+}
+__device__ __forceinline__ void snappy_locate(const SnappyGeom& g, uint32_t f, uint32_t* part, uint64_t* off, uint32_t* len) {
+    uint32_t p = g.frags_common ? f / g.frags_common : 0;
+    if (p >= g.T) p = g.T - 1;
+    const uint32_t j = f - p * g.frags_common;
+    const uint64_t pn = g.common + (p == g.T - 1 ? g.left : 0);
+    const uint64_t o = (uint64_t)j * kSnappyBlock;
+    *part = p; *off = g.common * p + o; *len = (uint32_t)min((uint64_t)kSnappyBlock, pn - o);
+}
+
+__global__ void __launch_bounds__(32) snappy_encode_frags_kernel(const uint8_t* __restrict__ src, SnappyGeom g,
+                                                                 uint8_t* scratch, uint64_t slot, uint32_t* frag_len) {
+    extern __shared__ __align__(16) uint32_t tab_mem[];
+    const int lane = lane_id();
+    const uint32_t f = blockIdx.x;
+    uint32_t part, len; uint64_t off;
+    snappy_locate(g, f, &part, &off, &len);
+    const uint32_t got = snappy_encode_fragment_warp(src + off, len, scratch + slot * f, reinterpret_cast<uint16_t*>(tab_mem), lane);
+    if (lane == 0) frag_len[f] = got;
+}
+
+// Step 2: offsets of every fragment in the final stream, RAP frame and the leading varint
+// (snappy.cc:2567-2651).  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) snappy_plan_kernel(SnappyGeom g, const uint32_t* __restrict__ frag_len,
+                                                           uint64_t* frag_off, uint8_t* dst, uint64_t out_cap,
+                                                           CallResult* res) {
+    __shared__ uint64_t sm[40];
+    const int tid = threadIdx.x;
+    const uint32_t F = g.frags_total;
+    const uint32_t per = (F + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(F, tid * per), hi = min(F, lo + per);
+    uint64_t local = 0;
+    for (uint32_t f = lo; f < hi; f++) local += frag_len[f];
+    uint64_t total = 0;
+    const bool framed = g.T > 1;
+    const uint64_t frame = framed ? (uint64_t)kRapHeaderBytes + (uint64_t)kRapEntryBytes * g.T : 0;
+    const uint64_t head = frame + varint32_len((uint32_t)g.n);
+    uint64_t base = head + block_excl_scan(local, &total, sm);
+    total += head;
+    const bool fits = total <= out_cap && total <= 0xffffffffull;
+    for (uint32_t f = lo; f < hi; f++) { frag_off[f] = base; base += frag_len[f]; }
+    __syncthreads();
+    if (!fits) { if (tid == 0) { res->error = 1; res->value = kErrCorrupt; } return; }
+    if (framed) {
+        for (uint32_t p = tid; p < g.T; p += blockDim.x) {      // RAP_i = {offset of body_i, |body_i|, part_i}
+            const uint32_t f0 = p * g.frags_common;
+            const uint32_t f1 = (p == g.T - 1) ? F : f0 + g.frags_common;
+            const uint64_t o0 = frag_off[f0];
+            const uint64_t o1 = frag_off[f1 - 1] + frag_len[f1 - 1];
+            uint8_t* e = dst + kRapHeaderBytes + (uint64_t)kRapEntryBytes * p;
+            st_u32_bytes(e, (uint32_t)o0); st_u32_bytes(e + 4, (uint32_t)(o1 - o0));
+            st_u32_bytes(e + 8, (uint32_t)(g.common + (p == g.T - 1 ? g.left : 0)));
+        }
+    }
+    if (tid == 0) {
+        if (framed) {
+            st_u32_bytes(dst, (uint32_t)kRapMagic); st_u32_bytes(dst + 4, (uint32_t)(kRapMagic >> 32));
+            st_u32_bytes(dst + 8, (uint32_t)frame); st_u32_bytes(dst + 12, g.T);
+        }
+        put_varint32(dst + frame, (uint32_t)g.n);               // snappy.cc:2617-2619
+        res->value = (long long)total;
+    }
+}
+
+// Step 3: compaction of the fragment bodies.
+__global__ void __launch_bounds__(256) snappy_compact_kernel(const uint8_t* __restrict__ scratch, uint64_t slot,
+                                                             const uint32_t* __restrict__ frag_len,
+                                                             const uint64_t* __restrict__ frag_off, uint8_t* dst,
+                                                             const CallResult* res) {
+    if (res->error) return;
+    const uint32_t f = blockIdx.x;
+    block_copy(dst + frag_off[f], scratch + slot * f, frag_len[f]);
+}
+
+}  // namespace llc

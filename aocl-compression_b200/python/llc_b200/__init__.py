@@ -1,0 +1,144 @@
+"""Python-side plumbing for the B200 LZ4/Snappy RAP library.
+
+The product is the C-ABI shared library ``aocl-compression_b200/lib/libaocl_compression.so``
+(sources in ``aocl-compression_b200/csrc``).  This package only *binds* it with ctypes so that
+tests and bench.py can drive it; torch is used by callers for device memory and
+torch.distributed, never on the data path.  There is no CPU fallback: if the library is
+missing or no CUDA device is usable, loading / calling fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # aocl-compression_b200/
+REPO_ROOT = os.path.dirname(PKG_DIR)
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libaocl_compression.so")
+
+LZ4, SNAPPY = 0, 4
+CODEC_NAMES = {LZ4: "lz4", SNAPPY: "snappy"}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into the in-tree shared library."""
+    subprocess.check_call(["make", "-C", PKG_DIR, "-j4"] + ([] if verbose else ["-s"]))
+    return LIB_PATH
+
+
+class AoclDesc(C.Structure):
+    """aocl_compression_desc (include/aocl_llc.h; reference api/aocl_compression.h:125-152)."""
+    _fields_ = [
+        ("inBuf", C.c_void_p), ("outBuf", C.c_void_p), ("workBuf", C.c_void_p),
+        ("inSize", C.c_size_t), ("outSize", C.c_size_t), ("level", C.c_size_t), ("optVar", C.c_size_t),
+        ("numThreads", C.c_int), ("numMPIranks", C.c_int), ("memLimit", C.c_size_t),
+        ("measureStats", C.c_int), ("cSize", C.c_uint64), ("dSize", C.c_uint64),
+        ("cTime", C.c_uint64), ("dTime", C.c_uint64), ("cSpeed", C.c_float), ("dSpeed", C.c_float),
+        ("optOff", C.c_int), ("optLevel", C.c_int),
+    ]
+
+
+HOST_API = ["aocl_llc_compress", "aocl_llc_decompress", "aocl_llc_setup", "aocl_llc_destroy", "aocl_llc_version",
+            "aocl_get_rap_frame_bound_mt", "aocl_skip_rap_frame_mt"]
+GPU_API = ["aocl_gpu_ctx_create", "aocl_gpu_ctx_destroy", "aocl_gpu_ctx_stream", "aocl_gpu_partition_count",
+           "aocl_gpu_compress_bound", "aocl_gpu_compress_async", "aocl_gpu_decompress_async", "aocl_gpu_finish",
+           "aocl_gpu_compress", "aocl_gpu_decompress", "aocl_gpu_set_lz4_frameless",
+           "aocl_gpu_decompress_range_async", "aocl_gpu_decompress_batch_async", "aocl_gpu_compress_batch_async",
+           "aocl_gpu_launch_count"]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the product library and declare every exported signature.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+    L = C.CDLL(LIB_PATH)
+    dp, vp, sz, i32, i64, u32, u64 = C.POINTER(AoclDesc), C.c_void_p, C.c_size_t, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64
+    sig = {
+        "aocl_llc_compress": (i64, [dp, C.c_int]), "aocl_llc_decompress": (i64, [dp, C.c_int]),
+        "aocl_llc_setup": (i32, [dp, C.c_int]), "aocl_llc_destroy": (None, [dp, C.c_int]),
+        "aocl_llc_version": (C.c_char_p, []), "aocl_get_rap_frame_bound_mt": (i32, []),
+        "aocl_skip_rap_frame_mt": (i32, [vp, i32]),
+        "aocl_gpu_ctx_create": (i32, [C.POINTER(vp), C.c_int, vp]), "aocl_gpu_ctx_destroy": (None, [vp]),
+        "aocl_gpu_ctx_stream": (vp, [vp]), "aocl_gpu_partition_count": (i32, [i32, sz]),
+        "aocl_gpu_compress_bound": (sz, [i32, sz]),
+        "aocl_gpu_compress_async": (i32, [vp, i32, vp, sz, vp, sz]),
+        "aocl_gpu_decompress_async": (i32, [vp, i32, vp, sz, vp, sz]),
+        "aocl_gpu_finish": (i64, [vp]),
+        "aocl_gpu_compress": (i64, [vp, i32, vp, sz, vp, sz]),
+        "aocl_gpu_decompress": (i64, [vp, i32, vp, sz, vp, sz]),
+        "aocl_gpu_set_lz4_frameless": (None, [vp, i32]),
+        "aocl_gpu_decompress_range_async": (i32, [vp, i32, vp, sz, vp, sz, u32, u32, u64]),
+        "aocl_gpu_decompress_batch_async": (i32, [vp, i32, vp, vp, vp, vp, vp, sz]),
+        "aocl_gpu_compress_batch_async": (i32, [vp, i32, vp, vp, vp, vp, vp, sz]),
+        "aocl_gpu_launch_count": (u64, []),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)     # AttributeError here == a declared symbol is not exported
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+class GpuContext:
+    """Thin RAII wrapper around aocl_gpu_ctx_t for torch callers (device pointers in, sizes out)."""
+
+    def __init__(self, device: int = -1, stream: int | None = None):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.aocl_gpu_ctx_create(C.byref(h), device, C.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise RuntimeError(f"aocl_gpu_ctx_create failed ({rc}): a CUDA device is required, there is no CPU fallback")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.aocl_gpu_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # tensors are torch.uint8 CUDA tensors; only data_ptr()/numel() are used
+    def compress_async(self, codec, src, dst):
+        return self.L.aocl_gpu_compress_async(self.h, codec, src.data_ptr(), src.numel(), dst.data_ptr(), dst.numel())
+
+    def decompress_async(self, codec, src, n, dst):
+        return self.L.aocl_gpu_decompress_async(self.h, codec, src.data_ptr(), n, dst.data_ptr(), dst.numel())
+
+    def decompress_range_async(self, codec, src, n, dst, first, count, origin):
+        return self.L.aocl_gpu_decompress_range_async(self.h, codec, src.data_ptr(), n, dst.data_ptr(), dst.numel(),
+                                                       first, count, origin)
+
+    def finish(self) -> int:
+        return self.L.aocl_gpu_finish(self.h)
+
+    def compress(self, codec, src, dst) -> int:
+        self.compress_async(codec, src, dst)
+        return self.finish()
+
+    def decompress(self, codec, src, n, dst) -> int:
+        self.decompress_async(codec, src, n, dst)
+        return self.finish()
+
+    def decompress_batch_async(self, codec, in_ptrs, in_sizes, out_ptrs, out_caps, status, count):
+        return self.L.aocl_gpu_decompress_batch_async(self.h, codec, in_ptrs.data_ptr(), in_sizes.data_ptr(),
+                                                       out_ptrs.data_ptr(), out_caps.data_ptr(), status.data_ptr(), count)
+
+    def compress_batch_async(self, codec, in_ptrs, in_sizes, out_ptrs, out_caps, status, count):
+        return self.L.aocl_gpu_compress_batch_async(self.h, codec, in_ptrs.data_ptr(), in_sizes.data_ptr(),
+                                                     out_ptrs.data_ptr(), out_caps.data_ptr(), status.data_ptr(), count)
+
+    def set_lz4_frameless(self, on: bool):
+        self.L.aocl_gpu_set_lz4_frameless(self.h, 1 if on else 0)
+
+    @property
+    def stream(self) -> int:
+        return self.L.aocl_gpu_ctx_stream(self.h)

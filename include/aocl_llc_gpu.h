@@ -1,0 +1,92 @@
+/*
+ * aocl_llc_gpu.h -- device-level entry points of the B200 LZ4 / Snappy RAP library.
+ *
+ * aocl_llc.h is the reference-facing API.  The functions here sit directly below it and
+ * are what aocl_llc_compress / aocl_llc_decompress call once their buffers are in HBM;
+ * they are exported so that callers that already hold device memory (a columnar reader,
+ * bench.py's device-resident leg, a multi-GPU driver that shards RAP partitions) can skip
+ * the PCIe staging.  Plain C ABI: pointers, sizes and a cudaStream_t passed as void*.
+ *
+ * Reference code each entry point replaces (paths under /root/reference):
+ *   aocl_gpu_compress      LZ4_compress_default -> AOCL_LZ4_compress_fast_mt   algos/lz4/lz4.c:2655-2909, 2967
+ *                          snappy::RawCompress                                algos/snappy/snappy.cc:2494-2666
+ *   aocl_gpu_decompress    LZ4_decompress_safe -> AOCL_LZ4_decompress_safe_mt  algos/lz4/lz4.c:4785-4890, 4898
+ *                          snappy::RawUncompress                              algos/snappy/snappy.cc:2271-2390
+ *   aocl_gpu_*_batch       a loop over LZ4_compress_default / LZ4_decompress_safe /
+ *                          snappy::RawCompress / RawUncompress on independent frame-less pages
+ *   aocl_gpu_partition_*   aocl_setup_parallel_compress_mt / aocl_do_partition_compress_mt
+ *                          threads/threads.c:46-153 (partition arithmetic only)
+ *
+ * Every function returns 0 / a byte count on success and a negative aocl_error_type-style
+ * code on failure.  No function falls back to the CPU.
+ */
+#ifndef AOCL_LLC_GPU_H
+#define AOCL_LLC_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AOCL_GPU_LZ4 0     /* == aocl_compression_type LZ4    */
+#define AOCL_GPU_SNAPPY 4  /* == aocl_compression_type SNAPPY */
+
+typedef struct aocl_gpu_ctx_s *aocl_gpu_ctx_t;
+
+/* One context = one CUDA stream + a growable HBM workspace + a pinned result block.
+ * `device` < 0 selects the current device.  `stream` NULL creates a private stream;
+ * otherwise work is enqueued on the caller's cudaStream_t. */
+int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t *ctx, int device, void *stream);
+void aocl_gpu_ctx_destroy(aocl_gpu_ctx_t ctx);
+void *aocl_gpu_ctx_stream(aocl_gpu_ctx_t ctx);
+
+/* RAP partition arithmetic for an n-byte input (saturated layout, T = P(n)). */
+int32_t aocl_gpu_partition_count(int32_t codec, size_t n);
+/* Worst-case compressed size incl. RAP frame, for sizing d_out. */
+size_t aocl_gpu_compress_bound(int32_t codec, size_t n);
+
+/* Whole-buffer operations on device-resident data.  d_in and d_out are device pointers.
+ * The *_async forms only enqueue; aocl_gpu_finish() synchronises the context's stream and
+ * returns the result of the most recent enqueue (bytes produced, or < 0). */
+int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in, size_t n,
+                                void *d_out, size_t out_cap);
+int32_t aocl_gpu_decompress_async(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in, size_t n,
+                                  void *d_out, size_t out_cap);
+int64_t aocl_gpu_finish(aocl_gpu_ctx_t ctx);
+int64_t aocl_gpu_compress(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in, size_t n,
+                          void *d_out, size_t out_cap);
+int64_t aocl_gpu_decompress(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in, size_t n,
+                            void *d_out, size_t out_cap);
+
+/* Frame-less single-partition LZ4 layout for every size (what the reference emits with
+ * optOff=1 or one OpenMP thread): 1 = on, 0 = off (default). */
+void aocl_gpu_set_lz4_frameless(aocl_gpu_ctx_t ctx, int32_t on);
+
+/* Decode only RAP partitions [first, first+count) of the stream at d_in into
+ * d_out + (sum of decomp_len of partitions < first) - out_origin.  Used to shard one frame
+ * across GPUs: each rank passes the same frame header and its own partition range.
+ * Result (bytes produced by the range) via aocl_gpu_finish(). */
+int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in, size_t n,
+                                        void *d_out, size_t out_cap, uint32_t first, uint32_t count,
+                                        uint64_t out_origin);
+
+/* Independent frame-less pages (one LZ4 block / one Snappy stream each), all device
+ * resident.  Arrays are device arrays of `count` entries.  status[i] receives bytes
+ * produced or < 0.  The return value of aocl_gpu_finish() is the number of failed pages
+ * negated (0 = all good). */
+int32_t aocl_gpu_decompress_batch_async(aocl_gpu_ctx_t ctx, int32_t codec, const void *const *d_in_ptrs,
+                                        const uint32_t *d_in_sizes, void *const *d_out_ptrs,
+                                        const uint32_t *d_out_caps, int64_t *d_status, size_t count);
+int32_t aocl_gpu_compress_batch_async(aocl_gpu_ctx_t ctx, int32_t codec, const void *const *d_in_ptrs,
+                                      const uint32_t *d_in_sizes, void *const *d_out_ptrs,
+                                      const uint32_t *d_out_caps, int64_t *d_status, size_t count);
+
+/* Number of kernels this library has launched in the calling process (bench.py reports it). */
+uint64_t aocl_gpu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AOCL_LLC_GPU_H */
