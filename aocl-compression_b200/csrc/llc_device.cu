@@ -11,11 +11,17 @@
 using namespace llc;
 
 static std::atomic<uint64_t> g_launches{0};
-#define LLC_LAUNCH(kernel, grid, block, smem, stream, ...)            \
-    do {                                                              \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);   \
-        g_launches.fetch_add(1, std::memory_order_relaxed);           \
+// Every launch goes through this macro: it counts the launch and, when profiling is enabled on
+// the context, brackets the kernel with CUDA events on the launching stream.
+#define LLC_LAUNCH(kernel, grid, block, smem, stream, ...)                         \
+    do {                                                                           \
+        const int prof_slot_ = prof_begin(c, #kernel);                             \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                \
+        prof_end(c, prof_slot_);                                                   \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                        \
     } while (0)
+
+constexpr int kProfSlots = 16;
 
 struct aocl_gpu_ctx_s {
     int device = 0;
@@ -30,7 +36,24 @@ struct aocl_gpu_ctx_s {
     bool lz4_frameless = false;
     bool batch_mode = false;        // last enqueue was a batch call (finish() returns -failures)
     int last_rc = 0;                // enqueue-time failure to report from finish()
+    // optional per-kernel timing (aocl_gpu_set_profiling)
+    bool prof = false;
+    int prof_n = 0;
+    cudaEvent_t prof_ev[kProfSlots][2] = {};
+    const char* prof_name[kProfSlots] = {};
 };
+
+static int prof_begin(aocl_gpu_ctx_t c, const char* name) {
+    if (!c->prof || c->prof_n >= kProfSlots) return -1;
+    const int s = c->prof_n++;
+    if (!c->prof_ev[s][0]) { cudaEventCreate(&c->prof_ev[s][0]); cudaEventCreate(&c->prof_ev[s][1]); }
+    c->prof_name[s] = name;
+    cudaEventRecord(c->prof_ev[s][0], c->stream);
+    return s;
+}
+static void prof_end(aocl_gpu_ctx_t c, int s) {
+    if (s >= 0) cudaEventRecord(c->prof_ev[s][1], c->stream);
+}
 
 static bool cuda_ok(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;
@@ -83,12 +106,22 @@ extern "C" void aocl_gpu_ctx_destroy(aocl_gpu_ctx_t c) {
     if (c->d_res) cudaFree(c->d_res);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    for (auto& e : c->prof_ev) { if (e[0]) cudaEventDestroy(e[0]); if (e[1]) cudaEventDestroy(e[1]); }
     delete c;
 }
 
 extern "C" void* aocl_gpu_ctx_stream(aocl_gpu_ctx_t c) { return c ? (void*)c->stream : nullptr; }
 extern "C" void aocl_gpu_set_lz4_frameless(aocl_gpu_ctx_t c, int32_t on) { if (c) c->lz4_frameless = on != 0; }
 extern "C" uint64_t aocl_gpu_launch_count(void) { return g_launches.load(); }
+extern "C" void aocl_gpu_set_profiling(aocl_gpu_ctx_t c, int32_t on) { if (c) c->prof = on != 0; }
+extern "C" int32_t aocl_gpu_profile_count(aocl_gpu_ctx_t c) { return c ? c->prof_n : 0; }
+extern "C" float aocl_gpu_profile_get(aocl_gpu_ctx_t c, int32_t i, char* name, int32_t name_cap) {
+    if (!c || i < 0 || i >= c->prof_n) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, c->prof_ev[i][0], c->prof_ev[i][1]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+    if (name && name_cap > 0) { strncpy(name, c->prof_name[i], name_cap - 1); name[name_cap - 1] = 0; }
+    return ms;
+}
 
 extern "C" int32_t aocl_gpu_partition_count(int32_t codec, size_t n) {
     return (int32_t)partition_count(n, codec == AOCL_GPU_LZ4 ? kLz4Window : kSnappyBlock);
@@ -105,6 +138,7 @@ static void begin_call(aocl_gpu_ctx_t c) {
     cudaMemsetAsync(c->d_res, 0, sizeof(CallResult), c->stream);
     c->batch_mode = false;
     c->last_rc = 0;
+    c->prof_n = 0;
 }
 static void end_call(aocl_gpu_ctx_t c) {
     cudaMemcpyAsync(c->h_res, c->d_res, sizeof(CallResult), cudaMemcpyDeviceToHost, c->stream);

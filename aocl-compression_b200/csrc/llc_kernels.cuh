@@ -4,6 +4,7 @@
 #include "llc_common.cuh"
 #include "lz4_codec.cuh"
 #include "snappy_codec.cuh"
+#include "lz4_decode_ring.cuh"
 
 namespace llc {
 
@@ -135,7 +136,10 @@ __global__ void __launch_bounds__(1024) rap_parse_kernel(int codec, const uint8_
 __global__ void __launch_bounds__(128) decode_parts_kernel(int codec, const uint8_t* __restrict__ in, uint8_t* out,
                                                            const PartDesc* __restrict__ parts, CallResult* res,
                                                            uint32_t first, uint32_t count, uint64_t origin) {
+    __shared__ RingStorage ring_mem[4];
     const int lane = lane_id();
+    Ring ring;
+    ring.init(&ring_mem[threadIdx.x >> 5], lane);
     if (res->error) return;
     const uint32_t T = (uint32_t)res->parts;
     const uint32_t end = min(T, first + min(count, T));
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(128) decode_parts_kernel(int codec, const uint
         if (d.in_len == 0) continue;
         uint8_t* dst = out + (d.out_off - origin);
         int64_t got;
-        if (codec == 0) got = lz4_decode_warp(in + d.in_off, d.in_len, dst, d.out_len, (d.flags & kPartLast) != 0, lane);
+        if (codec == 0) got = lz4_decode_warp_ring(ring, in + d.in_off, d.in_len, dst, d.out_len, (d.flags & kPartLast) != 0, lane);
         else            got = snappy_decode_warp(in + d.in_off, d.in_len, dst, d.out_len, lane);
         if (lane == 0) {
             if (got < 0 || ((d.flags & kPartExact) && (uint64_t)got != d.out_len)) atomicCAS(&res->error, 0, (int)i + 1);
@@ -181,13 +185,16 @@ __global__ void __launch_bounds__(128) decode_pages_kernel(int codec, const uint
                                                            const uint32_t* __restrict__ in_sizes, uint8_t* const* out_ptrs,
                                                            const uint32_t* __restrict__ out_caps, long long* status,
                                                            uint64_t count, CallResult* res) {
+    __shared__ RingStorage ring_mem[4];
     const int lane = lane_id();
+    Ring ring;
+    ring.init(&ring_mem[threadIdx.x >> 5], lane);
     const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += warps) {
         const uint8_t* in = in_ptrs[i];
         const uint32_t n = in_sizes[i], cap = out_caps[i];
         int64_t got;
-        if (codec == 0) got = lz4_decode_warp(in, n, out_ptrs[i], cap, true, lane);
+        if (codec == 0) got = lz4_decode_warp_ring(ring, in, n, out_ptrs[i], cap, true, lane);
         else {
             uint32_t total = 0;
             const uint32_t vb = get_varint32(in, n, &total);

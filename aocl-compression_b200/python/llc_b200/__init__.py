@@ -44,7 +44,7 @@ GPU_API = ["aocl_gpu_ctx_create", "aocl_gpu_ctx_destroy", "aocl_gpu_ctx_stream",
            "aocl_gpu_compress_bound", "aocl_gpu_compress_async", "aocl_gpu_decompress_async", "aocl_gpu_finish",
            "aocl_gpu_compress", "aocl_gpu_decompress", "aocl_gpu_set_lz4_frameless",
            "aocl_gpu_decompress_range_async", "aocl_gpu_decompress_batch_async", "aocl_gpu_compress_batch_async",
-           "aocl_gpu_launch_count"]
+           "aocl_gpu_launch_count", "aocl_gpu_set_profiling", "aocl_gpu_profile_count", "aocl_gpu_profile_get"]
 
 _lib = None
 
@@ -76,6 +76,8 @@ def load() -> C.CDLL:
         "aocl_gpu_decompress_batch_async": (i32, [vp, i32, vp, vp, vp, vp, vp, sz]),
         "aocl_gpu_compress_batch_async": (i32, [vp, i32, vp, vp, vp, vp, vp, sz]),
         "aocl_gpu_launch_count": (u64, []),
+        "aocl_gpu_set_profiling": (None, [vp, i32]), "aocl_gpu_profile_count": (i32, [vp]),
+        "aocl_gpu_profile_get": (C.c_float, [vp, i32, C.c_char_p, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)     # AttributeError here == a declared symbol is not exported
@@ -138,6 +140,18 @@ class GpuContext:
 
     def set_lz4_frameless(self, on: bool):
         self.L.aocl_gpu_set_lz4_frameless(self.h, 1 if on else 0)
+
+    def set_profiling(self, on: bool):
+        self.L.aocl_gpu_set_profiling(self.h, 1 if on else 0)
+
+    def profile(self) -> list[tuple[str, float]]:
+        """(kernel name, ms) of every kernel launched by the most recent enqueue (after finish())."""
+        out = []
+        buf = C.create_string_buffer(64)
+        for i in range(self.L.aocl_gpu_profile_count(self.h)):
+            ms = self.L.aocl_gpu_profile_get(self.h, i, buf, 64)
+            out.append((buf.value.decode(), float(ms)))
+        return out
 
     @property
     def stream(self) -> int:

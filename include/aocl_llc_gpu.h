@@ -86,6 +86,12 @@ int32_t aocl_gpu_compress_batch_async(aocl_gpu_ctx_t ctx, int32_t codec, const v
 /* Number of kernels this library has launched in the calling process (bench.py reports it). */
 uint64_t aocl_gpu_launch_count(void);
 
+/* Per-kernel device timing of the most recent enqueue: when enabled, every kernel launch is
+ * bracketed by CUDA events on the context's stream.  Query after aocl_gpu_finish(). */
+void aocl_gpu_set_profiling(aocl_gpu_ctx_t ctx, int32_t on);
+int32_t aocl_gpu_profile_count(aocl_gpu_ctx_t ctx);
+float aocl_gpu_profile_get(aocl_gpu_ctx_t ctx, int32_t index, char *name, int32_t name_cap);  /* ms, <0 if n/a */
+
 #ifdef __cplusplus
 }
 #endif
