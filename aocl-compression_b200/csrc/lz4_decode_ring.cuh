@@ -1,26 +1,30 @@
 // lz4_decode_ring.cuh -- pipelined warp-per-partition LZ4 decoder.
 //
 // Same accept/reject behaviour as lz4_decode_warp (lz4_codec.cuh; reference decoder
-// algos/lz4/lz4.c:3806-4305) but organised to keep global-memory latency off the
-// per-sequence dependency chain:
-//   * the compressed stream is read through a TMA-filled shared-memory ring (in_ring.cuh): one
-//     lane-parallel 32-byte window load yields the token, the short literal run and the match
-//     offset of a typical sequence;
-//   * literals go window -> HBM directly;
-//   * match copies of <= 32 bytes are software pipelined four deep: the back-reference load of
-//     sequence k is issued into a register and only stored when sequence k+4 needs the slot, so
-//     up to four L2 round trips overlap with the parsing of the following sequences.  A match whose
-//     source overlaps a still-pending destination flushes the pipeline first.
+// algos/lz4/lz4.c:3806-4305), organised so that neither global-memory latency nor instruction
+// count sits on the per-sequence dependency chain:
+//   * the compressed stream is read through a TMA-filled shared-memory ring (in_ring.cuh);
+//   * FAST PATH (a sequence whose token, optional single length bytes, <= 27 literals and offset fit
+//     one 32-byte window, match <= 32 bytes, no self-overlap, far from both buffer ends): three
+//     shared loads give the window byte per lane, the token and the first length byte; the next
+//     sequence's loads are issued as soon as the token tells where it starts (software prefetch),
+//     so the serial chain per sequence is LDS -> a few ALU ops -> LDS; literals go window -> HBM;
+//     the match is a single byte-per-lane load that is only stored four sequences later
+//     (register pipeline, hazard-checked against pending destinations), so up to four L2 round
+//     trips overlap with parsing;
+//   * everything else (length runs, long literals / matches, overlapping matches, the last bytes
+//     of a partition, malformed input) takes lz4_slow_sequence(): flush the pipeline and run the
+//     fully checked general code once.
 #pragma once
 #include "in_ring.cuh"
 
 namespace llc {
 
 // Reads a 255-terminated length extension starting at ring position p (lz4.c:3330-3352).
-// Returns the added value and advances p; bad is set on truncated input.
 __device__ __forceinline__ uint32_t lz4_ring_ext(Ring& r, uint32_t& p, uint32_t iend, bool& bad, int lane) {
     uint32_t add = 0;
     for (;;) {
+        if ((p >> kChunkLog) != r.w0) r.advance(p, lane);
         r.ensure(p + 32);
         const uint32_t q = p + lane;
         const uint32_t b = q < iend ? r.byte(q) : 0u;          // a 0 past the end stops the scan there
@@ -35,85 +39,114 @@ __device__ __forceinline__ uint32_t lz4_ring_ext(Ring& r, uint32_t& p, uint32_t 
         add += 255u * 32u;
         p += 32;
         if (add > 0x7fff0000u) { bad = true; return add; }
-        r.advance(p, lane);
     }
 }
 
-#define LLC_PEND_STORE(S)                                                         \
-    if (pmask & (1u << S)) { if ((uint32_t)lane < pl##S) out[pd##S + lane] = (uint8_t)pv##S; }
-#define LLC_FLUSH()                                                               \
-    do { LLC_PEND_STORE(0) LLC_PEND_STORE(1) LLC_PEND_STORE(2) LLC_PEND_STORE(3)  \
-         pmask = 0; pend_lo = 0xffffffffu; } while (0)
-
-// One sequence; S is the pipeline slot this sequence's match uses.
-#define LLC_LZ4_SEQ(S)                                                                                      \
-    {                                                                                                       \
-        if (ip >= iend) goto corrupt;                                                                       \
-        if ((ip >> kChunkLog) != r.w0 || r.w1 == r.w0) r.advance(ip, lane);                                 \
-        r.ensure(ip + 40);                                                                                  \
-        const uint32_t w = r.byte(ip + lane);                                                               \
-        const uint32_t tok = __shfl_sync(kFull, w, 0);                                                      \
-        uint32_t ll = tok >> 4;                                                                             \
-        uint32_t p = ip + 1;                                                                                \
-        bool bad = false;                                                                                   \
-        if (ll == 15) { ll += lz4_ring_ext(r, p, iend, bad, lane); if (bad) goto corrupt; }                 \
-        if (ll > iend - p || ll > cap - op) goto corrupt;                                                   \
-        const bool closing = ((uint64_t)op + ll + 12 > cap) || ((uint64_t)p + ll + 8 > iend);               \
-        if (closing && last && p + ll != iend) goto corrupt;                                                \
-        bool in_window = (p == ip + 1) && (ll <= 29);                                                       \
-        if (in_window) {                                                                                    \
-            if (lane >= 1 && (uint32_t)lane <= ll) out[op + lane - 1] = (uint8_t)w;                         \
-        } else if (ll <= 512) {                                                                             \
-            r.ensure(p + ll + 8);                                                                           \
-            for (uint32_t k = lane; k < ll; k += 32) out[op + k] = (uint8_t)r.byte(p + k);                  \
-        } else {                                                                                            \
-            warp_copy(out + op, r.gbase + p, ll, lane);                                                     \
-        }                                                                                                   \
-        op += ll;                                                                                           \
-        const uint32_t q = p + ll;          /* position of the match offset */                              \
-        if (closing && (last || op == cap)) { ip = q; goto done; }                                          \
-        if (q == iend) { ip = q; goto done; }                                                               \
-        if (q + 2 > iend) goto corrupt;                                                                     \
-        uint32_t off;                                                                                       \
-        if (in_window) {                                                                                    \
-            off = __shfl_sync(kFull, w, (int)(q - ip)) | (__shfl_sync(kFull, w, (int)(q - ip) + 1) << 8);   \
-        } else {                                                                                            \
-            if ((q >> kChunkLog) != r.w0) r.advance(q, lane);                                               \
-            r.ensure(q + 40);                                                                               \
-            off = r.byte(q) | (r.byte(q + 1) << 8);                                                         \
-        }                                                                                                   \
-        ip = q + 2;                                                                                         \
-        uint32_t ml = tok & 15;                                                                             \
-        if (ml == 15) { ml += lz4_ring_ext(r, ip, iend, bad, lane); if (bad) goto corrupt; }                \
-        ml += 4;                                                                                            \
-        if (off == 0 || off > op) goto corrupt;                                                             \
-        if (ml > cap - op) goto corrupt;                                                                    \
-        if (last && (uint64_t)op + ml + 5 > cap) goto corrupt;                                              \
-        if (ml <= 32) {                                                                                     \
-            const uint32_t src = op - off;                                                                  \
-            if (src + min(ml, off) > pend_lo) LLC_FLUSH();                                                  \
-            LLC_PEND_STORE(S)                                                                               \
-            pmask &= ~(1u << S);                                                                            \
-            __syncwarp();                   /* earlier stores of this warp are ordered before the load */  \
-            uint32_t k = lane;              /* overlapping match: periodic pattern of period off */      \
-            if (off < ml) k = lane - off * __float2uint_rz(__fdividef((float)lane + 0.5f, (float)off));     \
-            pv##S = ((uint32_t)lane < ml) ? out[src + k] : 0;                                               \
-            pd##S = op; pl##S = ml;                                                                         \
-            if (pmask == 0) pend_lo = op;                                                                   \
-            else pend_lo = (pmask >> ((S + 1) & 3) & 1u) ? LLC_PD((S + 1) & 3)                              \
-                         : (pmask >> ((S + 2) & 3) & 1u) ? LLC_PD((S + 2) & 3) : LLC_PD((S + 3) & 3);       \
-            pmask |= 1u << S;                                                                               \
-        } else {                                                                                            \
-            LLC_FLUSH();                                                                                    \
-            __syncwarp();                                                                                   \
-            warp_match_copy(out, op, off, ml, lane);                                                        \
-            __syncwarp();                                                                                   \
-        }                                                                                                   \
-        op += ml;                                                                                           \
-        if (!last && (op == cap || ip >= iend)) goto done;                                                  \
+// One fully checked sequence without pipelining.  Returns 0: continue, 1: stream finished, -1: corrupt.
+__device__ __noinline__ int lz4_slow_sequence(Ring* rp, uint32_t* ip_io, uint32_t* op_io, uint8_t* out, uint32_t iend,
+                                              uint32_t cap, bool last, int lane) {
+    Ring& r = *rp;
+    uint32_t ip = *ip_io, op = *op_io;
+    if (ip >= iend) return -1;
+    if ((ip >> kChunkLog) != r.w0 || r.w1 == r.w0) r.advance(ip, lane);
+    r.ensure(ip + 40);
+    const uint32_t tok = r.byte(ip);
+    uint32_t ll = tok >> 4;
+    uint32_t p = ip + 1;
+    bool bad = false;
+    if (ll == 15) { ll += lz4_ring_ext(r, p, iend, bad, lane); if (bad) return -1; }
+    if (ll > iend - p || ll > cap - op) return -1;
+    // end-of-block parsing restrictions, lz4.c:4104-4164
+    const bool closing = ((uint64_t)op + ll + 12 > cap) || ((uint64_t)p + ll + 8 > iend);
+    if (closing && last && p + ll != iend) return -1;
+    if (ll <= 512) {
+        if ((p >> kChunkLog) != r.w0) r.advance(p, lane);
+        r.ensure(p + ll + 8);
+        for (uint32_t k = lane; k < ll; k += 32) out[op + k] = (uint8_t)r.byte(p + k);
+    } else {
+        warp_copy(out + op, r.gbase + p, ll, lane);
     }
+    op += ll;
+    const uint32_t q = p + ll;
+    *op_io = op;
+    if (closing && (last || op == cap)) { *ip_io = q; return 1; }
+    if (q == iend) { *ip_io = q; return 1; }
+    if (q + 2 > iend) return -1;
+    if ((q >> kChunkLog) != r.w0) r.advance(q, lane);
+    r.ensure(q + 40);
+    const uint32_t off = r.byte(q) | (r.byte(q + 1) << 8);
+    ip = q + 2;
+    uint32_t ml = tok & 15;
+    if (ml == 15) { ml += lz4_ring_ext(r, ip, iend, bad, lane); if (bad) return -1; }
+    ml += 4;
+    if (off == 0 || off > op) return -1;                               // lz4.c:4196-4197
+    if (ml > cap - op) return -1;
+    if (last && (uint64_t)op + ml + 5 > cap) return -1;                // lz4.c:4262-4264
+    __syncwarp();
+    warp_match_copy(out, op, off, ml, lane);
+    __syncwarp();
+    op += ml;
+    *ip_io = ip; *op_io = op;
+    if (!last && (op == cap || ip >= iend)) return 1;                  // lz4.c:4285-4288
+    return 0;
+}
 
-#define LLC_PD(i) ((i) == 0 ? pd0 : (i) == 1 ? pd1 : (i) == 2 ? pd2 : pd3)
+// Keeps the ring window starting at the chunk of `low` (the sequence being executed; the ring never
+// moves backwards) and waits until a 40-byte window at `need` has landed.  Returns the two
+// thresholds the fast loop tests: a current position >= *chunk_end means chunks can be recycled,
+// a prefetch position > *safe_end means data may still be in flight.
+__device__ __noinline__ void lz4_ring_maintain(Ring* rp, uint32_t low, uint32_t need, uint32_t* chunk_end,
+                                               uint32_t* safe_end, int lane) {
+    Ring& r = *rp;
+    if ((low >> kChunkLog) != r.w0 || r.w1 == r.w0) r.advance(low, lane);
+    r.ensure(need + 40);
+    *chunk_end = (r.w0 + 1) << kChunkLog;
+    *safe_end = (r.wr >= r.nchunks) ? 0xffffffffu : ((r.wr << kChunkLog) - 40u);
+}
+
+#define LLC_PEND_STORE(S) { if ((uint32_t)lane < pl##S) out[pd##S + lane] = (uint8_t)pv##S; }
+#define LLC_FLUSH()                                                                          \
+    do { LLC_PEND_STORE(0) LLC_PEND_STORE(1) LLC_PEND_STORE(2) LLC_PEND_STORE(3)             \
+         pl0 = pl1 = pl2 = pl3 = 0; pd0 = pd1 = pd2 = pd3 = 0xffffffffu; pend_lo = 0xffffffffu; } while (0)
+#define LLC_LOAD_WINDOW(pos)                                                                 \
+    do { w = sbase[((pos) + lane) & kRingMask]; tok = sbase[(pos) & kRingMask]; e1 = sbase[((pos) + 1) & kRingMask]; } while (0)
+
+#define LLC_LZ4_SEQ(S, A, B, C)                                                                              \
+    {                                                                                                        \
+        const uint32_t nibL = tok >> 4, nibM = tok & 15u;                                                    \
+        const uint32_t extL = (nibL == 15u) ? 1u : 0u, extM = (nibM == 15u) ? 1u : 0u;                       \
+        const uint32_t ll = nibL + (extL ? e1 : 0u);                                                         \
+        const uint32_t hdr = 1u + extL;                                                                      \
+        const uint32_t qpos = hdr + ll;                     /* window index of the offset */                 \
+        const uint32_t ipn = ip + qpos + 2u + extM;                                                          \
+        const uint32_t w_cur = w;                                                                            \
+        /* prefetch the next sequence's window while this one is being executed */                          \
+        if (ip >= chunk_end || ipn > safe_end) lz4_ring_maintain(&r, ip, ipn, &chunk_end, &safe_end, lane);  \
+        LLC_LOAD_WINDOW(ipn);                                                                                \
+        const uint32_t off = __shfl_sync(kFull, w_cur, (int)qpos) | (__shfl_sync(kFull, w_cur, (int)qpos + 1) << 8); \
+        const uint32_t e2 = __shfl_sync(kFull, w_cur, (int)qpos + 2);                                        \
+        const uint32_t ml = 4u + nibM + (extM ? e2 : 0u);                                                    \
+        const uint32_t op2 = op + ll;                                                                        \
+        const bool fast = (ll <= 27u) & (ml <= 32u) & (off >= ml) & (off <= op2) & (ip <= fast_i) & (op <= fast_o); \
+        if (!fast) {                                                                                         \
+            LLC_FLUSH();                                                                                     \
+            const int st = lz4_slow_sequence(&r, &ip, &op, out, iend, cap, last, lane);                      \
+            if (st != 0) { status = st; break; }                                                             \
+            lz4_ring_maintain(&r, ip, ip, &chunk_end, &safe_end, lane);                                      \
+            LLC_LOAD_WINDOW(ip);                                                                             \
+            continue;                                                                                        \
+        }                                                                                                    \
+        if ((uint32_t)lane - hdr < ll) out[op + lane - hdr] = (uint8_t)w_cur;                                \
+        const uint32_t src = op2 - off;                                                                      \
+        if (src + ml > pend_lo) LLC_FLUSH();                                                                 \
+        LLC_PEND_STORE(S)                                                                                    \
+        __syncwarp();                       /* earlier stores of this warp are ordered before the load */   \
+        pv##S = ((uint32_t)lane < ml) ? out[src + lane] : 0;                                                 \
+        pd##S = op2; pl##S = ml;                                                                             \
+        pend_lo = min(min(pd##A, pd##B), min(pd##C, op2));                                                   \
+        op = op2 + ml;                                                                                       \
+        ip = ipn;                                                                                            \
+    }
 
 // `out` points at the partition's first output byte; offsets inside the partition fit 32 bits.
 __device__ inline int64_t lz4_decode_warp_ring(Ring& r, const uint8_t* __restrict__ in, uint32_t clen, uint8_t* out,
@@ -122,24 +155,34 @@ __device__ inline int64_t lz4_decode_warp_ring(Ring& r, const uint8_t* __restric
     if (cap == 0) return (clen == 1 && in[0] == 0) ? 0 : kErrCorrupt;   // lz4.c:3854-3858
     uint32_t ip = r.open(in, clen);
     const uint32_t iend = r.total;
+    const uint8_t* sbase = r.sm;
+    const uint32_t fast_i = iend >= 40u ? iend - 40u : 0u;
+    const uint32_t fast_o = cap >= 72u ? cap - 72u : 0u;
+    const bool any_fast = iend >= 40u + ip && cap >= 72u;
     uint32_t op = 0;
-    uint32_t pmask = 0, pend_lo = 0xffffffffu;
+    uint32_t pend_lo = 0xffffffffu;
     uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0;
-    uint32_t pd0 = 0, pd1 = 0, pd2 = 0, pd3 = 0;
+    uint32_t pd0 = 0xffffffffu, pd1 = 0xffffffffu, pd2 = 0xffffffffu, pd3 = 0xffffffffu;
     uint32_t pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0;
-    for (;;) {
-        LLC_LZ4_SEQ(0)
-        LLC_LZ4_SEQ(1)
-        LLC_LZ4_SEQ(2)
-        LLC_LZ4_SEQ(3)
+    uint32_t chunk_end = 0, safe_end = 0;
+    uint32_t w, tok, e1;
+    int status = 0;
+    lz4_ring_maintain(&r, ip, ip, &chunk_end, &safe_end, lane);
+    LLC_LOAD_WINDOW(ip);
+    if (!any_fast) {
+        // tiny stream: every sequence through the checked path
+        while ((status = lz4_slow_sequence(&r, &ip, &op, out, iend, cap, last, lane)) == 0) {}
+    } else {
+        for (;;) {
+            LLC_LZ4_SEQ(0, 1, 2, 3)
+            LLC_LZ4_SEQ(1, 2, 3, 0)
+            LLC_LZ4_SEQ(2, 3, 0, 1)
+            LLC_LZ4_SEQ(3, 0, 1, 2)
+        }
     }
-done:
     LLC_FLUSH();
     r.close();
-    return (int64_t)op;
-corrupt:
-    r.close();
-    return kErrCorrupt;
+    return status > 0 ? (int64_t)op : kErrCorrupt;
 }
 
 }  // namespace llc
