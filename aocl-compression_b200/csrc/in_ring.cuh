@@ -41,8 +41,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// explicit shared-space byte load (keeps ring reads on the LDS path with 32-bit addresses)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 struct RingStorage {
-    alignas(128) uint8_t data[kRingBytes];
+    alignas(kRingBytes) uint8_t data[kRingBytes];       // ring-size aligned: address = base | (pos & mask)
     alignas(8) uint64_t bar[kStages];
 };
 
@@ -56,8 +63,9 @@ struct Ring {
     uint32_t par;             // per-slot parity of the next phase to wait for (persists across streams)
 
     // once per warp, before the first stream
-    __device__ __forceinline__ void init(RingStorage* st, int lane) {
-        sm = st->data; bar = st->bar; par = 0;
+    __device__ __forceinline__ void init(RingStorage* st, int lane) { init(st->data, st->bar, lane); }
+    __device__ __forceinline__ void init(uint8_t* data, uint64_t* bars, int lane) {
+        sm = data; bar = bars; par = 0;
         if (lane == 0) {
             for (uint32_t s = 0; s < kStages; s++) mbar_init(&bar[s], 1);
             fence_mbar_init();

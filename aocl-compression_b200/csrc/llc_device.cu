@@ -33,6 +33,9 @@ struct aocl_gpu_ctx_s {
     CallResult* d_res = nullptr;    // result block on the device
     CallResult* h_res = nullptr;    // pinned mirror
     int decode_blocks = 0;          // persistent grid size of decode_parts_kernel
+    int ws_blocks = 0;              // persistent grid size of decode_parts_ws_kernel
+    int decoder_mode = 0;           // 0: LZ4 single-warp ring decoder, Snappy two-warp decoder (default);
+                                    // 1: single-warp everywhere (AOCL_GPU_DECODER=warp); 2: two-warp everywhere (=ws)
     bool lz4_frameless = false;
     bool batch_mode = false;        // last enqueue was a batch call (finish() returns -failures)
     int last_rc = 0;                // enqueue-time failure to report from finish()
@@ -94,6 +97,11 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_parts_kernel, 128, 0);
     if (per_sm < 1) per_sm = 1;
     c->decode_blocks = per_sm * c->sm_count;
+    per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_parts_ws_kernel, 64, 0);
+    if (per_sm < 1) per_sm = 1;
+    c->ws_blocks = per_sm * c->sm_count;
+    if (const char* e = getenv("AOCL_GPU_DECODER")) c->decoder_mode = strcmp(e, "warp") == 0 ? 1 : strcmp(e, "ws") == 0 ? 2 : 0;
     *out = c;
     return 0;
 }
@@ -171,8 +179,13 @@ extern "C" int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t c, int32_t cod
     // for a range the capacity check applies to the range, not to the whole stream
     LLC_LAUNCH(rap_parse_kernel, 1, 1024, 0, c->stream, codec, (const uint8_t*)d_in, (uint64_t)n,
                ranged ? ~0ull : (uint64_t)out_cap, parts, c->d_res);
-    LLC_LAUNCH(decode_parts_kernel, c->decode_blocks, 128, 0, c->stream, codec, (const uint8_t*)d_in, (uint8_t*)d_out,
-               parts, c->d_res, first, count, out_origin);
+    const bool warp_decoder = c->decoder_mode == 1 || (c->decoder_mode == 0 && codec == AOCL_GPU_LZ4);
+    if (warp_decoder)
+        LLC_LAUNCH(decode_parts_kernel, c->decode_blocks, 128, 0, c->stream, codec, (const uint8_t*)d_in, (uint8_t*)d_out,
+                   parts, c->d_res, first, count, out_origin);
+    else
+        LLC_LAUNCH(decode_parts_ws_kernel, c->ws_blocks, 64, 0, c->stream, codec, (const uint8_t*)d_in, (uint8_t*)d_out,
+                   parts, c->d_res, first, count, out_origin);
     if (ranged) LLC_LAUNCH(range_total_kernel, 1, 256, 0, c->stream, parts, c->d_res, first, count);
     end_call(c);
     return 0;
@@ -254,10 +267,17 @@ extern "C" int32_t aocl_gpu_decompress_batch_async(aocl_gpu_ctx_t c, int32_t cod
         c->last_rc = -2; return -2;
     }
     if (count) {
-        const uint64_t blocks = (count + 3) / 4;
-        const int grid = (int)(blocks < (uint64_t)c->decode_blocks * 4 ? blocks : (uint64_t)c->decode_blocks * 4);
-        LLC_LAUNCH(decode_pages_kernel, grid, 128, 0, c->stream, codec, (const uint8_t* const*)d_in_ptrs, d_in_sizes,
-                   (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status, (uint64_t)count, c->d_res);
+        const bool warp_decoder = c->decoder_mode == 1 || (c->decoder_mode == 0 && codec == AOCL_GPU_LZ4);
+        if (warp_decoder) {
+            const uint64_t blocks = (count + 3) / 4;
+            const int grid = (int)(blocks < (uint64_t)c->decode_blocks * 4 ? blocks : (uint64_t)c->decode_blocks * 4);
+            LLC_LAUNCH(decode_pages_kernel, grid, 128, 0, c->stream, codec, (const uint8_t* const*)d_in_ptrs, d_in_sizes,
+                       (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status, (uint64_t)count, c->d_res);
+        } else {
+            const int grid = (int)(count < (uint64_t)c->ws_blocks * 2 ? count : (uint64_t)c->ws_blocks * 2);
+            LLC_LAUNCH(decode_pages_ws_kernel, grid, 64, 0, c->stream, codec, (const uint8_t* const*)d_in_ptrs, d_in_sizes,
+                       (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status, (uint64_t)count, c->d_res);
+        }
     }
     end_call(c);
     return 0;

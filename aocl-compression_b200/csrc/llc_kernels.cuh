@@ -5,6 +5,7 @@
 #include "lz4_codec.cuh"
 #include "snappy_codec.cuh"
 #include "lz4_decode_ring.cuh"
+#include "decode_wspec.cuh"
 
 namespace llc {
 
@@ -158,6 +159,64 @@ __global__ void __launch_bounds__(128) decode_parts_kernel(int codec, const uint
             if (got < 0 || ((d.flags & kPartExact) && (uint64_t)got != d.out_len)) atomicCAS(&res->error, 0, (int)i + 1);
             else if (!(d.flags & kPartExact)) res->value = got;     // frame-less LZ4: size is whatever was produced
         }
+    }
+}
+
+// Warp-specialised variant (decode_wspec.cuh): one CTA of two warps (parser + copier) per partition,
+// partitions handed out through the same atomic ticket.
+__global__ void __launch_bounds__(64, 24) decode_parts_ws_kernel(int codec, const uint8_t* __restrict__ in, uint8_t* out,
+                                                                 const PartDesc* __restrict__ parts, CallResult* res,
+                                                                 uint32_t first, uint32_t count, uint64_t origin) {
+    LLC_WS_SHARED(sh);
+    const int lane = lane_id();
+    Ring ring;
+    if (threadIdx.x < 32) ring.init(ws_ring_data(sh), sh.ring_bar, lane);
+    __syncthreads();
+    if (res->error) return;
+    const uint32_t T = (uint32_t)res->parts;
+    const uint32_t end = min(T, first + min(count, T));
+    for (;;) {
+        if (threadIdx.x == 0) sh.unit = first + atomicAdd(&res->next, 1u);
+        __syncthreads();
+        const uint32_t i = sh.unit;
+        __syncthreads();
+        if (i >= end) break;
+        const PartDesc d = parts[i];
+        if (d.in_len == 0) continue;
+        const int64_t got = ws_decode_unit(&sh, ring, codec, in + d.in_off, d.in_len, out + (d.out_off - origin), d.out_len,
+                                           (d.flags & kPartLast) != 0);
+        if (threadIdx.x == 0) {
+            if (got < 0 || ((d.flags & kPartExact) && (uint64_t)got != d.out_len)) atomicCAS(&res->error, 0, (int)i + 1);
+            else if (!(d.flags & kPartExact)) res->value = got;     // frame-less LZ4: size is whatever was produced
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64, 24) decode_pages_ws_kernel(int codec, const uint8_t* const* __restrict__ in_ptrs,
+                                                                 const uint32_t* __restrict__ in_sizes, uint8_t* const* out_ptrs,
+                                                                 const uint32_t* __restrict__ out_caps, long long* status,
+                                                                 uint64_t count, CallResult* res) {
+    LLC_WS_SHARED(sh);
+    const int lane = lane_id();
+    Ring ring;
+    if (threadIdx.x < 32) ring.init(ws_ring_data(sh), sh.ring_bar, lane);
+    __syncthreads();
+    for (uint64_t i = blockIdx.x; i < count; i += gridDim.x) {
+        const uint8_t* in = in_ptrs[i];
+        const uint32_t n = in_sizes[i], cap = out_caps[i];
+        int64_t got;
+        if (codec == 0) got = ws_decode_unit(&sh, ring, 0, in, n, out_ptrs[i], cap, true);
+        else {
+            uint32_t total = 0;
+            const uint32_t vb = get_varint32(in, n, &total);
+            if (vb == 0 || total > cap) got = kErrCorrupt;
+            else got = ws_decode_unit(&sh, ring, 4, in + vb, n - vb, out_ptrs[i], total, true);
+        }
+        if (threadIdx.x == 0) {
+            status[i] = got;
+            if (got < 0) atomicAdd(&res->error, 1);
+        }
+        __syncthreads();
     }
 }
 

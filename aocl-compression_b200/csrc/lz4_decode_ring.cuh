@@ -42,23 +42,24 @@ __device__ __forceinline__ uint32_t lz4_ring_ext(Ring& r, uint32_t& p, uint32_t 
     }
 }
 
-// One fully checked sequence without pipelining.  Returns 0: continue, 1: stream finished, -1: corrupt.
-__device__ __noinline__ int lz4_slow_sequence(Ring* rp, uint32_t* ip_io, uint32_t* op_io, uint8_t* out, uint32_t iend,
-                                              uint32_t cap, bool last, int lane) {
+// One fully checked sequence without pipelining.  status 0: continue, 1: stream finished, -1: corrupt.
+// State goes in and out by value so that the caller's hot-loop variables stay in registers.
+struct Lz4Step { int status; uint32_t ip, op; };
+__device__ __noinline__ Lz4Step lz4_slow_sequence(Ring* rp, uint32_t ip, uint32_t op, uint8_t* out, uint32_t iend,
+                                                  uint32_t cap, bool last, int lane) {
     Ring& r = *rp;
-    uint32_t ip = *ip_io, op = *op_io;
-    if (ip >= iend) return -1;
+    if (ip >= iend) return Lz4Step{-1, ip, op};
     if ((ip >> kChunkLog) != r.w0 || r.w1 == r.w0) r.advance(ip, lane);
     r.ensure(ip + 40);
     const uint32_t tok = r.byte(ip);
     uint32_t ll = tok >> 4;
     uint32_t p = ip + 1;
     bool bad = false;
-    if (ll == 15) { ll += lz4_ring_ext(r, p, iend, bad, lane); if (bad) return -1; }
-    if (ll > iend - p || ll > cap - op) return -1;
+    if (ll == 15) { ll += lz4_ring_ext(r, p, iend, bad, lane); if (bad) return Lz4Step{-1, ip, op}; }
+    if (ll > iend - p || ll > cap - op) return Lz4Step{-1, ip, op};
     // end-of-block parsing restrictions, lz4.c:4104-4164
     const bool closing = ((uint64_t)op + ll + 12 > cap) || ((uint64_t)p + ll + 8 > iend);
-    if (closing && last && p + ll != iend) return -1;
+    if (closing && last && p + ll != iend) return Lz4Step{-1, ip, op};
     if (ll <= 512) {
         if ((p >> kChunkLog) != r.w0) r.advance(p, lane);
         r.ensure(p + ll + 8);
@@ -68,48 +69,50 @@ __device__ __noinline__ int lz4_slow_sequence(Ring* rp, uint32_t* ip_io, uint32_
     }
     op += ll;
     const uint32_t q = p + ll;
-    *op_io = op;
-    if (closing && (last || op == cap)) { *ip_io = q; return 1; }
-    if (q == iend) { *ip_io = q; return 1; }
-    if (q + 2 > iend) return -1;
+    if (closing && (last || op == cap)) return Lz4Step{1, q, op};
+    if (q == iend) return Lz4Step{1, q, op};
+    if (q + 2 > iend) return Lz4Step{-1, q, op};
     if ((q >> kChunkLog) != r.w0) r.advance(q, lane);
     r.ensure(q + 40);
     const uint32_t off = r.byte(q) | (r.byte(q + 1) << 8);
     ip = q + 2;
     uint32_t ml = tok & 15;
-    if (ml == 15) { ml += lz4_ring_ext(r, ip, iend, bad, lane); if (bad) return -1; }
+    if (ml == 15) { ml += lz4_ring_ext(r, ip, iend, bad, lane); if (bad) return Lz4Step{-1, ip, op}; }
     ml += 4;
-    if (off == 0 || off > op) return -1;                               // lz4.c:4196-4197
-    if (ml > cap - op) return -1;
-    if (last && (uint64_t)op + ml + 5 > cap) return -1;                // lz4.c:4262-4264
+    if (off == 0 || off > op) return Lz4Step{-1, ip, op};              // lz4.c:4196-4197
+    if (ml > cap - op) return Lz4Step{-1, ip, op};
+    if (last && (uint64_t)op + ml + 5 > cap) return Lz4Step{-1, ip, op};   // lz4.c:4262-4264
     __syncwarp();
     warp_match_copy(out, op, off, ml, lane);
     __syncwarp();
     op += ml;
-    *ip_io = ip; *op_io = op;
-    if (!last && (op == cap || ip >= iend)) return 1;                  // lz4.c:4285-4288
-    return 0;
+    if (!last && (op == cap || ip >= iend)) return Lz4Step{1, ip, op};  // lz4.c:4285-4288
+    return Lz4Step{0, ip, op};
 }
 
 // Keeps the ring window starting at the chunk of `low` (the sequence being executed; the ring never
 // moves backwards) and waits until a 40-byte window at `need` has landed.  Returns the two
 // thresholds the fast loop tests: a current position >= *chunk_end means chunks can be recycled,
 // a prefetch position > *safe_end means data may still be in flight.
-__device__ __noinline__ void lz4_ring_maintain(Ring* rp, uint32_t low, uint32_t need, uint32_t* chunk_end,
-                                               uint32_t* safe_end, int lane) {
+__device__ __noinline__ uint64_t lz4_ring_maintain(Ring* rp, uint32_t low, uint32_t need, int lane) {
     Ring& r = *rp;
     if ((low >> kChunkLog) != r.w0 || r.w1 == r.w0) r.advance(low, lane);
     r.ensure(need + 40);
-    *chunk_end = (r.w0 + 1) << kChunkLog;
-    *safe_end = (r.wr >= r.nchunks) ? 0xffffffffu : ((r.wr << kChunkLog) - 40u);
+    const uint32_t chunk_end = (r.w0 + 1) << kChunkLog;
+    const uint32_t safe_end = (r.wr >= r.nchunks) ? 0xffffffffu : ((r.wr << kChunkLog) - 40u);
+    return (uint64_t)chunk_end | ((uint64_t)safe_end << 32);
 }
+#define LLC_MAINTAIN(low, need)                                                              \
+    do { const uint64_t th_ = lz4_ring_maintain(&r, (low), (need), lane);                    \
+         chunk_end = (uint32_t)th_; safe_end = (uint32_t)(th_ >> 32); } while (0)
 
 #define LLC_PEND_STORE(S) { if ((uint32_t)lane < pl##S) out[pd##S + lane] = (uint8_t)pv##S; }
 #define LLC_FLUSH()                                                                          \
     do { LLC_PEND_STORE(0) LLC_PEND_STORE(1) LLC_PEND_STORE(2) LLC_PEND_STORE(3)             \
          pl0 = pl1 = pl2 = pl3 = 0; pd0 = pd1 = pd2 = pd3 = 0xffffffffu; pend_lo = 0xffffffffu; } while (0)
 #define LLC_LOAD_WINDOW(pos)                                                                 \
-    do { w = sbase[((pos) + lane) & kRingMask]; tok = sbase[(pos) & kRingMask]; e1 = sbase[((pos) + 1) & kRingMask]; } while (0)
+    do { w = lds_u8(sbase + (((pos) + lane) & kRingMask)); tok = lds_u8(sbase + ((pos) & kRingMask));       \
+         e1 = lds_u8(sbase + (((pos) + 1) & kRingMask)); } while (0)
 
 #define LLC_LZ4_SEQ(S, A, B, C)                                                                              \
     {                                                                                                        \
@@ -121,7 +124,7 @@ __device__ __noinline__ void lz4_ring_maintain(Ring* rp, uint32_t low, uint32_t 
         const uint32_t ipn = ip + qpos + 2u + extM;                                                          \
         const uint32_t w_cur = w;                                                                            \
         /* prefetch the next sequence's window while this one is being executed */                          \
-        if (ip >= chunk_end || ipn > safe_end) lz4_ring_maintain(&r, ip, ipn, &chunk_end, &safe_end, lane);  \
+        if (ip >= chunk_end || ipn > safe_end) LLC_MAINTAIN(ip, ipn);                                        \
         LLC_LOAD_WINDOW(ipn);                                                                                \
         const uint32_t off = __shfl_sync(kFull, w_cur, (int)qpos) | (__shfl_sync(kFull, w_cur, (int)qpos + 1) << 8); \
         const uint32_t e2 = __shfl_sync(kFull, w_cur, (int)qpos + 2);                                        \
@@ -130,9 +133,10 @@ __device__ __noinline__ void lz4_ring_maintain(Ring* rp, uint32_t low, uint32_t 
         const bool fast = (ll <= 27u) & (ml <= 32u) & (off >= ml) & (off <= op2) & (ip <= fast_i) & (op <= fast_o); \
         if (!fast) {                                                                                         \
             LLC_FLUSH();                                                                                     \
-            const int st = lz4_slow_sequence(&r, &ip, &op, out, iend, cap, last, lane);                      \
-            if (st != 0) { status = st; break; }                                                             \
-            lz4_ring_maintain(&r, ip, ip, &chunk_end, &safe_end, lane);                                      \
+            const Lz4Step st = lz4_slow_sequence(&r, ip, op, out, iend, cap, last, lane);                    \
+            ip = st.ip; op = st.op;                                                                          \
+            if (st.status != 0) { status = st.status; break; }                                               \
+            LLC_MAINTAIN(ip, ip);                                                                            \
             LLC_LOAD_WINDOW(ip);                                                                             \
             continue;                                                                                        \
         }                                                                                                    \
@@ -155,7 +159,7 @@ __device__ inline int64_t lz4_decode_warp_ring(Ring& r, const uint8_t* __restric
     if (cap == 0) return (clen == 1 && in[0] == 0) ? 0 : kErrCorrupt;   // lz4.c:3854-3858
     uint32_t ip = r.open(in, clen);
     const uint32_t iend = r.total;
-    const uint8_t* sbase = r.sm;
+    const uint32_t sbase = smem_u32(r.sm);
     const uint32_t fast_i = iend >= 40u ? iend - 40u : 0u;
     const uint32_t fast_o = cap >= 72u ? cap - 72u : 0u;
     const bool any_fast = iend >= 40u + ip && cap >= 72u;
@@ -167,11 +171,14 @@ __device__ inline int64_t lz4_decode_warp_ring(Ring& r, const uint8_t* __restric
     uint32_t chunk_end = 0, safe_end = 0;
     uint32_t w, tok, e1;
     int status = 0;
-    lz4_ring_maintain(&r, ip, ip, &chunk_end, &safe_end, lane);
+    LLC_MAINTAIN(ip, ip);
     LLC_LOAD_WINDOW(ip);
     if (!any_fast) {
         // tiny stream: every sequence through the checked path
-        while ((status = lz4_slow_sequence(&r, &ip, &op, out, iend, cap, last, lane)) == 0) {}
+        do {
+            const Lz4Step st = lz4_slow_sequence(&r, ip, op, out, iend, cap, last, lane);
+            ip = st.ip; op = st.op; status = st.status;
+        } while (status == 0);
     } else {
         for (;;) {
             LLC_LZ4_SEQ(0, 1, 2, 3)
