@@ -27,6 +27,16 @@ struct aocl_gpu_ctx_s {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;    // second stream for kernels that run concurrently with the main one
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // LZ4 encoder placement.  Every partition is one serial chain, so wall time is (waves) x (chain
+    // latency): what matters is having ALL partitions resident at once.  Up to 14 x SMs partitions the
+    // shared-memory-table flavour does that with the fastest table; beyond, only the global-table
+    // flavour (32 warps per SM, tables L2 resident) keeps a 1 GiB frame (4094 partitions) in one wave.
+    // Measured on B200, 1 GiB text: 14 smem CTAs/SM = 100 ms, 14 smem + 16 gtab = 75 ms, 32 gtab = 54 ms.
+    int gtab_ctas_per_sm = -1;      // AOCL_GPU_GTAB_CTAS: global-table CTAs per SM (-1 auto, 0 never)
+    int stab_ctas_per_sm = -1;      // AOCL_GPU_STAB_CTAS: shared-table CTAs per SM (-1 auto, 0 never; max 14)
+    int snappy_gtab_ctas_per_sm = -1;   // AOCL_GPU_SNAPPY_GTAB_CTAS: Snappy global-table CTAs per SM (-1 auto, 0 never)
     int sm_count = 0;
     uint8_t* ws = nullptr;          // growable HBM workspace (scratch slots, tables, plans)
     size_t ws_bytes = 0;
@@ -88,6 +98,13 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     if (!cuda_ok(cudaMalloc(&c->d_res, sizeof(CallResult)), "cudaMalloc(result)") ||
         !cuda_ok(cudaMallocHost(&c->h_res, sizeof(CallResult)), "cudaMallocHost(result)")) { aocl_gpu_ctx_destroy(c); return -2; }
     memset(c->h_res, 0, sizeof(CallResult));
+    cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    if (const char* e = getenv("AOCL_GPU_GTAB_CTAS")) c->gtab_ctas_per_sm = atoi(e);
+    if (const char* e = getenv("AOCL_GPU_SNAPPY_GTAB_CTAS")) c->snappy_gtab_ctas_per_sm = atoi(e);
+    if (const char* e = getenv("AOCL_GPU_STAB_CTAS")) c->stab_ctas_per_sm = atoi(e) > 14 ? 14 : atoi(e);
+
     // opt in to the shared-memory sizes the encoders need (16 KiB LZ4 table, 32 KiB Snappy table)
     cudaFuncSetAttribute(lz4_encode_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
     cudaFuncSetAttribute(lz4_encode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
@@ -114,6 +131,9 @@ extern "C" void aocl_gpu_ctx_destroy(aocl_gpu_ctx_t c) {
     if (c->d_res) cudaFree(c->d_res);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (auto& e : c->prof_ev) { if (e[0]) cudaEventDestroy(e[0]); if (e[1]) cudaEventDestroy(e[1]); }
     delete c;
 }
@@ -220,13 +240,42 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
         } else {
             const uint64_t pmax = n / T + n % T;
             const uint64_t slot = align_up(pmax + pmax / 255 + 32, 256);
-            const size_t o_rec = 0, o_plan = align_up(o_rec + sizeof(Lz4Rec) * T, 256);
-            const size_t o_scr = align_up(o_plan + sizeof(Lz4Plan) * T, 256);
+            int stab = c->stab_ctas_per_sm, gtab = c->gtab_ctas_per_sm;
+            if (stab < 0 && gtab < 0) {                        // auto: one wave if at all possible
+                if (T <= (uint32_t)c->sm_count * 14u) { stab = 14; gtab = 0; } else { stab = 0; gtab = 32; }
+            }
+            if (stab < 0) stab = gtab > 0 ? 0 : 14;
+            if (gtab < 0) gtab = 0;
+            if (stab == 0 && gtab == 0) stab = 14;
+            const int g_ctas = gtab * c->sm_count;
+            const size_t o_rec = 0, o_plan = align_up(o_rec + sizeof(Lz4Rec) * T + 256, 256);
+            const size_t o_tab = align_up(o_plan + sizeof(Lz4Plan) * T, 256);
+            const size_t o_scr = align_up(o_tab + (size_t)g_ctas * 16384, 256);
             if (!ensure_ws(c, o_scr + slot * T)) { c->last_rc = -2; return -2; }
             Lz4Rec* rec = reinterpret_cast<Lz4Rec*>(c->ws + o_rec);
+            uint32_t* ticket = reinterpret_cast<uint32_t*>(c->ws + o_rec + sizeof(Lz4Rec) * T);
             Lz4Plan* plan = reinterpret_cast<Lz4Plan*>(c->ws + o_plan);
+            uint32_t* tables = reinterpret_cast<uint32_t*>(c->ws + o_tab);
             uint8_t* scratch = c->ws + o_scr;
-            LLC_LAUNCH(lz4_encode_parts_kernel, T, 32, 16384, c->stream, src, (uint64_t)n, T, scratch, slot, rec);
+            cudaMemsetAsync(ticket, 0, sizeof(uint32_t), c->stream);
+            const uint32_t a_cap = (uint32_t)c->sm_count * (uint32_t)stab;
+            const int a_grid = (int)(T < a_cap ? T : a_cap);
+            const int enc_slot = prof_begin(c, "lz4_encode_parts_kernel");   // brackets both flavours (fork .. join)
+            if (g_ctas > 0 && T > (uint32_t)a_grid) {
+                // fork: the global-table flavour shares the ticket and fills the idle warp slots
+                cudaEventRecord(c->ev_fork, c->stream);
+                cudaStreamWaitEvent(c->side, c->ev_fork, 0);
+                lz4_encode_parts_gtab_kernel<<<(int)(T < (uint32_t)g_ctas ? T : (uint32_t)g_ctas), 32, 0, c->side>>>(
+                    src, (uint64_t)n, T, scratch, slot, rec, ticket, tables);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                cudaEventRecord(c->ev_join, c->side);
+            }
+            if (a_grid > 0) {
+                lz4_encode_parts_kernel<<<a_grid, 32, 16384, c->stream>>>(src, (uint64_t)n, T, scratch, slot, rec, ticket);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+            }
+            if (g_ctas > 0 && T > (uint32_t)a_grid) cudaStreamWaitEvent(c->stream, c->ev_join, 0);
+            prof_end(c, enc_slot);
             LLC_LAUNCH(lz4_stitch_plan_kernel, 1, 1024, 0, c->stream, scratch, slot, rec, (uint64_t)n, T, dst,
                        (uint64_t)out_cap, plan, c->d_res);
             LLC_LAUNCH(lz4_compact_kernel, T, 256, 0, c->stream, src, scratch, slot, rec, plan, dst, c->d_res);
@@ -237,13 +286,24 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
         const SnappyGeom g = snappy_geom(n, T);
         const uint32_t F = g.frags_total;
         const uint64_t slot = 76544;                           // >= 32 + 65536 + 65536/6, multiple of 256
-        const size_t o_len = 0, o_off = align_up(o_len + sizeof(uint32_t) * (F + 1), 256);
-        const size_t o_scr = align_up(o_off + sizeof(uint64_t) * (F + 1), 256);
+        // same placement rule as the LZ4 encoder: fragments are serial chains, the 32 KiB table caps
+        // the shared-memory flavour at 7 warps per SM, the global-table flavour runs snappy_gtab per SM
+        int sn_gtab = c->snappy_gtab_ctas_per_sm;
+        if (sn_gtab < 0) sn_gtab = F > (uint32_t)c->sm_count * 7u ? 16 : 0;   // measured: 0 -> 74 ms, 16 -> 60 ms, 32 -> 78 ms (L2 thrash)
+        const uint32_t g_grid = (uint32_t)sn_gtab * (uint32_t)c->sm_count < F ? (uint32_t)sn_gtab * (uint32_t)c->sm_count : F;
+        const size_t o_len = 0, o_off = align_up(o_len + sizeof(uint32_t) * (F + 2), 256);
+        const size_t o_tab = align_up(o_off + sizeof(uint64_t) * (F + 1), 256);
+        const size_t o_scr = align_up(o_tab + (size_t)g_grid * 32768, 256);
         if (!ensure_ws(c, o_scr + slot * (F + 1))) { c->last_rc = -2; return -2; }
         uint32_t* frag_len = reinterpret_cast<uint32_t*>(c->ws + o_len);
+        uint32_t* ticket = frag_len + F + 1;
         uint64_t* frag_off = reinterpret_cast<uint64_t*>(c->ws + o_off);
+        uint16_t* tables = reinterpret_cast<uint16_t*>(c->ws + o_tab);
         uint8_t* scratch = c->ws + o_scr;
-        if (F) LLC_LAUNCH(snappy_encode_frags_kernel, F, 32, 32768, c->stream, src, g, scratch, slot, frag_len);
+        cudaMemsetAsync(ticket, 0, sizeof(uint32_t), c->stream);
+        if (F && g_grid) LLC_LAUNCH(snappy_encode_frags_gtab_kernel, g_grid, 32, 0, c->stream, src, g, scratch, slot, frag_len, ticket, tables);
+        else if (F) LLC_LAUNCH(snappy_encode_frags_kernel, (F < (uint32_t)c->sm_count * 7u ? F : (uint32_t)c->sm_count * 7u), 32, 32768,
+                               c->stream, src, g, scratch, slot, frag_len, ticket);
         LLC_LAUNCH(snappy_plan_kernel, 1, 1024, 0, c->stream, g, frag_len, frag_off, dst, (uint64_t)out_cap, c->d_res);
         if (F) LLC_LAUNCH(snappy_compact_kernel, F, 256, 0, c->stream, scratch, slot, frag_len, frag_off, dst, c->d_res);
     }

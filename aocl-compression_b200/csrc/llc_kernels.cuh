@@ -310,16 +310,37 @@ __global__ void __launch_bounds__(32) encode_pages_kernel(int codec, const uint8
 // ------------------------------------------------------------------------------------------
 struct Lz4Rec { uint32_t body_len; uint32_t tail_len; };
 
-__global__ void __launch_bounds__(32) lz4_encode_parts_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
-                                                              uint8_t* scratch, uint64_t slot, Lz4Rec* rec) {
-    extern __shared__ __align__(16) uint32_t tab_mem[];
+// Persistent: CTAs (one warp each) draw partitions from a shared ticket.  Two flavours run
+// CONCURRENTLY on two streams: the shared-memory flavour is capped at 14 warps per SM by its
+// 16 KiB table, and leaves most issue slots idle because every warp is a serial dependency chain;
+// the global-memory flavour keeps its table in an L2-resident workspace slice (no shared memory),
+// so its warps fill the remaining warp slots of each SM.  Both produce identical bytes.
+__device__ __forceinline__ void lz4_encode_parts_loop(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
+                                                      uint8_t* scratch, uint64_t slot, Lz4Rec* rec, uint32_t* ticket,
+                                                      uint32_t* tab_mem) {
     const int lane = lane_id();
-    const uint32_t i = blockIdx.x;
     const uint64_t common = n / T, left = n % T;             // threads/threads.c:91-97,127-135
-    const uint32_t pn = (uint32_t)(common + (i == T - 1 ? left : 0));
-    uint32_t tail = 0;
-    const uint32_t body = lz4_encode_warp(src + common * i, pn, scratch + slot * i, -1, i == T - 1, &tail, tab_mem, lane);
-    if (lane == 0) { rec[i].body_len = body; rec[i].tail_len = tail; }
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(ticket, 1u);
+        i = __shfl_sync(kFull, i, 0);
+        if (i >= T) break;
+        const uint32_t pn = (uint32_t)(common + (i == T - 1 ? left : 0));
+        uint32_t tail = 0;
+        const uint32_t body = lz4_encode_warp(src + common * i, pn, scratch + slot * i, -1, i == T - 1, &tail, tab_mem, lane);
+        if (lane == 0) { rec[i].body_len = body; rec[i].tail_len = tail; }
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(32) lz4_encode_parts_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
+                                                              uint8_t* scratch, uint64_t slot, Lz4Rec* rec, uint32_t* ticket) {
+    extern __shared__ __align__(16) uint32_t tab_mem[];
+    lz4_encode_parts_loop(src, n, T, scratch, slot, rec, ticket, tab_mem);
+}
+__global__ void __launch_bounds__(32) lz4_encode_parts_gtab_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
+                                                                   uint8_t* scratch, uint64_t slot, Lz4Rec* rec,
+                                                                   uint32_t* ticket, uint32_t* tables) {
+    lz4_encode_parts_loop(src, n, T, scratch, slot, rec, ticket, tables + (size_t)blockIdx.x * 4096);
 }
 
 // Frame-less block written straight to the destination (T == 1, lz4.c:2674-2677).
@@ -502,15 +523,31 @@ __device__ __forceinline__ void snappy_locate(const SnappyGeom& g, uint32_t f, u
     *part = p; *off = g.common * p + o; *len = (uint32_t)min((uint64_t)kSnappyBlock, pn - o);
 }
 
-__global__ void __launch_bounds__(32) snappy_encode_frags_kernel(const uint8_t* __restrict__ src, SnappyGeom g,
-                                                                 uint8_t* scratch, uint64_t slot, uint32_t* frag_len) {
-    extern __shared__ __align__(16) uint32_t tab_mem[];
+__device__ __forceinline__ void snappy_encode_frags_loop(const uint8_t* __restrict__ src, const SnappyGeom& g, uint8_t* scratch,
+                                                         uint64_t slot, uint32_t* frag_len, uint32_t* ticket, uint16_t* tab) {
     const int lane = lane_id();
-    const uint32_t f = blockIdx.x;
-    uint32_t part, len; uint64_t off;
-    snappy_locate(g, f, &part, &off, &len);
-    const uint32_t got = snappy_encode_fragment_warp(src + off, len, scratch + slot * f, reinterpret_cast<uint16_t*>(tab_mem), lane);
-    if (lane == 0) frag_len[f] = got;
+    for (;;) {
+        uint32_t f = 0;
+        if (lane == 0) f = atomicAdd(ticket, 1u);
+        f = __shfl_sync(kFull, f, 0);
+        if (f >= g.frags_total) break;
+        uint32_t part, len; uint64_t off;
+        snappy_locate(g, f, &part, &off, &len);
+        const uint32_t got = snappy_encode_fragment_warp(src + off, len, scratch + slot * f, tab, lane);
+        if (lane == 0) frag_len[f] = got;
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(32) snappy_encode_frags_kernel(const uint8_t* __restrict__ src, SnappyGeom g,
+                                                                 uint8_t* scratch, uint64_t slot, uint32_t* frag_len,
+                                                                 uint32_t* ticket) {
+    extern __shared__ __align__(16) uint32_t tab_mem[];
+    snappy_encode_frags_loop(src, g, scratch, slot, frag_len, ticket, reinterpret_cast<uint16_t*>(tab_mem));
+}
+__global__ void __launch_bounds__(32) snappy_encode_frags_gtab_kernel(const uint8_t* __restrict__ src, SnappyGeom g,
+                                                                      uint8_t* scratch, uint64_t slot, uint32_t* frag_len,
+                                                                      uint32_t* ticket, uint16_t* tables) {
+    snappy_encode_frags_loop(src, g, scratch, slot, frag_len, ticket, tables + (size_t)blockIdx.x * 16384);
 }
 
 // Step 2: offsets of every fragment in the final stream, RAP frame and the leading varint

@@ -250,11 +250,205 @@ __device__ inline uint32_t lz4_encode_warp_impl(const uint8_t* __restrict__ src,
     return op + 1 + ext + run;
 }
 
+// -------------------------------------------------------------------------------------------
+// Encoder, fused-round version.  Same parse as lz4_encode_warp_impl, reorganised so that one
+// sequence costs two dependent global round trips instead of six:
+//   * every lane loads a 12-byte window [p-4, p+8) around its probe position and, after the table
+//     lookup, around its candidate; from the two windows it derives locally whether the candidate
+//     verifies, how far the match extends backwards (catch-up, up to 4 bytes) and forwards (up to 8
+//     bytes).  Only longer extensions take the extra compare rounds;
+//   * the probe of the position right after a match (lz4.c:2230-2288: insert ip-2, test ip) is
+//     slot 0 of the next 32-probe round, followed by the first 31 probes of the next search.
+// -------------------------------------------------------------------------------------------
+struct Lz4Win { uint32_t back, lo, hi; };      // bytes [p-4,p), [p,p+4), [p+4,p+8); back is 0 when p < 4
+__device__ __forceinline__ Lz4Win lz4_load_win(const uint8_t* src, uint32_t pos) {
+    const uint32_t o = pos >= 4u ? 4u : 0u;
+    const uint8_t* p = src + pos - o;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    const uint32_t x = __funnelshift_r(w0, w1, sh), y = __funnelshift_r(w1, w2, sh), z = __funnelshift_r(w2, w3, sh);
+    Lz4Win r;
+    if (o) { r.back = x; r.lo = y; r.hi = z; } else { r.back = 0; r.lo = x; r.hi = y; }
+    return r;
+}
+
+template <bool WIDE>
+__device__ inline uint32_t lz4_encode_warp_fused(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, int64_t cap,
+                                                 bool emit_tail, uint32_t* tail_len, uint32_t* tab_mem, int lane) {
+    Lz4Table<WIDE> tab{tab_mem};
+    for (int i = lane; i < 4096; i += 32) tab_mem[i] = 0;
+    __syncwarp();
+    const bool limited = cap >= 0;
+    uint32_t op = 0, anchor = 0;
+    bool refused = false;
+
+    if (n >= 13) {                                          // LZ4_minLength, lz4.c:1926
+        const uint32_t mfl1 = n - 11;                       // mflimitPlusOne, lz4.c:1887
+        const uint32_t mlimit = n - 5;                      // matchlimit, lz4.c:1888
+        tab.put(tab.hash(src), 0);                          // lz4.c:1929
+        __syncwarp();
+        bool post = false;                                  // slot 0 is the probe right after a match
+        uint32_t base = 0;                                  // post rounds: position of slot 0
+        uint32_t fwd = 1, step = 1, nb = 64;                // search schedule (lz4.c:1991-1997)
+        for (;;) {
+            // ---------------- one round of 32 probe slots in serial order ----------------
+            uint32_t cur, nxt;
+            bool valid;
+            if (post) { cur = base + lane; nxt = cur + 1; valid = (lane == 0) || (nxt <= mfl1); }
+            else {
+                const uint32_t my_step = (lane == 0) ? step : ((nb + lane - 1) >> 6);
+                const uint32_t incl = warp_incl_sum(my_step, lane);
+                cur = fwd + incl - my_step; nxt = fwd + incl;
+                valid = nxt <= mfl1;                        // lz4.c:2001
+            }
+            Lz4Win cw = {0, 0, 0};
+            uint32_t h = 0x80000000u | lane;
+            if (valid) {
+                cw = lz4_load_win(src, cur);
+                h = WIDE ? lz4_hash5((uint64_t)cw.lo | ((uint64_t)cw.hi << 32)) : lz4_hash4(cw.lo);
+            }
+            if (post) {                                     // lz4.c:2230: insert ip-2 before anything else
+                if (lane == 0) {
+                    // bytes [base-2, base+6) out of the window [base-4, base+8)
+                    const uint64_t v = ((uint64_t)(cw.back >> 16)) | ((uint64_t)cw.lo << 16) | ((uint64_t)cw.hi << 48);
+                    tab.put(WIDE ? lz4_hash5(v) : lz4_hash4((uint32_t)v), base - 2);
+                }
+                __syncwarp();
+            }
+            uint32_t cand = valid ? tab.get(h) : 0u;
+            const unsigned peers = __match_any_sync(kFull, h);
+            const unsigned before = peers & ((1u << lane) - 1u);
+            const int from = before ? (31 - __clz(before)) : lane;
+            const uint32_t peer_pos = __shfl_sync(kFull, cur, from);
+            if (before) cand = peer_pos;
+            bool hit = false;
+            uint32_t bk = 0, fw = 0;                        // locally known backward / forward extension
+            bool more_b = false, more_f = false;
+            if (valid) {
+                const Lz4Win mw = lz4_load_win(src, cand);
+                hit = (mw.lo == cw.lo) && (!WIDE || cur - cand <= 65535u);      // lz4.c:2048-2057
+                // forward: bytes [p+4, p+8), bounded by matchlimit
+                const uint32_t xf = cw.hi ^ mw.hi;
+                const uint32_t eqf = xf ? ((uint32_t)(__ffs(xf) - 1) >> 3) : 4u;
+                const uint32_t roomf = mlimit > cur + 4u ? mlimit - (cur + 4u) : 0u;
+                fw = min(eqf, roomf);
+                more_f = (eqf == 4u) && (roomf > 4u);
+                // backward: bytes [p-4, p) from the top, bounded by the anchor and by position 0 (lz4.c:2098)
+                const uint32_t bwin = (cur >= 4u && cand >= 4u) ? 4u : 0u;
+                const uint32_t xb = cw.back ^ mw.back;
+                const uint32_t eqb = bwin ? (xb ? ((uint32_t)__clz(xb) >> 3) : 4u) : 0u;
+                const uint32_t roomb = min(cur - anchor, cand);
+                bk = min(eqb, roomb);
+                more_b = (eqb == bwin) && (roomb > bwin);
+            }
+            const unsigned hits = __ballot_sync(kFull, hit);
+            const unsigned events = hits | __ballot_sync(kFull, !valid);
+            const int win = events ? (__ffs(events) - 1) : 32;
+            const bool win_is_match = (win < 32) && ((hits >> win) & 1u);
+            const unsigned commit = (win_is_match ? (win == 31 ? kFull : ((2u << win) - 1u))
+                                                  : (win == 0 ? 0u : (win >= 32 ? kFull : ((1u << win) - 1u))));
+            if (valid && ((commit >> lane) & 1u)) {
+                const unsigned mine = peers & commit;
+                if ((31 - __clz(mine)) == lane) tab.put(h, cur);
+            }
+            __syncwarp();
+            if (win >= 32) {                                // nothing happened: next 32 probes of the same search
+                if (post) { fwd = base + 32; step = 1; nb = 64 + 31; post = false; }
+                else { fwd = __shfl_sync(kFull, nxt, 31); step = (nb + 31) >> 6; nb += 32; }
+                continue;
+            }
+            if (!win_is_match) break;                       // search ran into the end of the block -> closing literals
+
+            // ---------------- the winner's match ----------------
+            const uint32_t mpos = __shfl_sync(kFull, cur, win);
+            const uint32_t mcand = __shfl_sync(kFull, cand, win);
+            uint32_t back = __shfl_sync(kFull, bk, win);
+            uint32_t mc = __shfl_sync(kFull, fw, win);
+            const bool go_b = __shfl_sync(kFull, (int)more_b, win) != 0;
+            const bool go_f = __shfl_sync(kFull, (int)more_f, win) != 0;
+            const bool from_search = !(post && win == 0);   // slot 0 of a post round: zero literals, no catch-up
+            uint32_t ip = mpos - back, m = mcand - back;
+            if (go_b && from_search) {                      // rare: catch-up longer than the window
+                for (;;) {
+                    const bool can = (ip > anchor + lane) && (m > (uint32_t)lane);
+                    const bool eq = can && (src[ip - 1 - lane] == src[m - 1 - lane]);
+                    const unsigned ne = __ballot_sync(kFull, !eq);
+                    const uint32_t cnt = ne ? (uint32_t)(__ffs(ne) - 1) : 32u;
+                    ip -= cnt; m -= cnt; back += cnt;
+                    if (cnt < 32) break;
+                }
+            }
+            if (go_f) {                                     // match longer than 8: 128 bytes per extra round (lz4.c:656-679)
+                const uint32_t delta = mpos - mcand;
+                uint32_t pb = mpos + 8;
+                for (;;) {
+                    const uint32_t pa = pb + 4u * lane;
+                    uint32_t c = 0;
+                    if (pa < mlimit) {
+                        const uint32_t avail = min(4u, mlimit - pa);
+                        const uint32_t x = ld_u32(src + pa) ^ ld_u32(src + pa - delta);
+                        c = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+                        c = min(c, avail);
+                    }
+                    const unsigned partial = __ballot_sync(kFull, c < 4);
+                    if (partial) {
+                        const int first = __ffs(partial) - 1;
+                        mc += 4u * first + __shfl_sync(kFull, c, first);
+                        break;
+                    }
+                    mc += 128; pb += 128;
+                }
+            }
+            const uint32_t ll = ip - anchor;
+            const uint32_t code = mc + back;                // match length - 4, counted from the caught-up start
+            // ---- emit: token | literal-length bytes | literals | offset | match-length bytes
+            const uint32_t ll_ext = ll >= 15 ? (ll - 15) / 255 + 1 : 0;
+            const uint32_t ml_ext = code >= 15 ? (code - 15) / 255 + 1 : 0;
+            if (limited) {
+                // lz4.c:2104-2107 (literals) and lz4.c:2177-2204 (match length)
+                if (from_search && (int64_t)op + 1 + ll + 8 + ll / 255 > cap) { refused = true; break; }
+                if ((int64_t)op + 1 + ll_ext + ll + 2 + 6 + (code + 240) / 255 > cap) { refused = true; break; }
+            }
+            if (lane == 0) dst[op] = (uint8_t)((min(ll, 15u) << 4) | min(code, 15u));
+            if (ll_ext) lz4_put_ext(dst + op + 1, ll - 15, lane);
+            if (ll <= 32) { if ((uint32_t)lane < ll) dst[op + 1 + ll_ext + lane] = src[anchor + lane]; }
+            else warp_copy(dst + op + 1 + ll_ext, src + anchor, ll, lane);
+            op += 1 + ll_ext + ll;
+            if (lane == 0) { dst[op] = (uint8_t)(ip - m); dst[op + 1] = (uint8_t)((ip - m) >> 8); }
+            op += 2;
+            if (ml_ext) lz4_put_ext(dst + op, code - 15, lane);
+            op += ml_ext;
+
+            base = mpos + 4 + mc;                           // first position after the match
+            anchor = base;
+            if (base >= mfl1) break;                        // lz4.c:2227
+            post = true;
+        }
+    }
+    if (refused) return 0;
+    const uint32_t run = n - anchor;
+    if (!emit_tail) { if (tail_len) *tail_len = run; return op; }        // lz4.c:2333-2338
+    if (tail_len) *tail_len = 0;
+    if (limited && (int64_t)op + run + 1 + (run + 255 - 15) / 255 > cap) return 0;   // lz4.c:2299-2311
+    const uint32_t ext = run >= 15 ? (run - 15) / 255 + 1 : 0;
+    if (lane == 0) dst[op] = (uint8_t)(min(run, 15u) << 4);
+    if (ext) lz4_put_ext(dst + op + 1, run - 15, lane);
+    warp_copy(dst + op + 1 + ext, src + anchor, run, lane);
+    return op + 1 + ext + run;
+}
+
 __device__ inline uint32_t lz4_encode_warp(const uint8_t* src, uint32_t n, uint8_t* dst, int64_t cap, bool emit_tail,
                                            uint32_t* tail_len, uint32_t* tab_mem, int lane) {
     if (n == 0) { if (lane == 0) dst[0] = 0; if (tail_len) *tail_len = 0; return 1; }   // lz4.c:2418-2428
+#ifdef LLC_LZ4_ENCODER_SIMPLE
     if (n >= 65547) return lz4_encode_warp_impl<true>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane);
     return lz4_encode_warp_impl<false>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane);
+#else
+    if (n >= 65547) return lz4_encode_warp_fused<true>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane);
+    return lz4_encode_warp_fused<false>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane);
+#endif
 }
 
 }  // namespace llc
