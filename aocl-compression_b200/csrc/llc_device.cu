@@ -44,8 +44,11 @@ struct aocl_gpu_ctx_s {
     CallResult* h_res = nullptr;    // pinned mirror
     int decode_blocks = 0;          // persistent grid size of decode_parts_kernel
     int ws_blocks = 0;              // persistent grid size of decode_parts_ws_kernel
-    int decoder_mode = 0;           // 0: LZ4 single-warp ring decoder, Snappy two-warp decoder (default);
-                                    // 1: single-warp everywhere (AOCL_GPU_DECODER=warp); 2: two-warp everywhere (=ws)
+    // Decoder organisation (AOCL_GPU_DECODER).  Measured on B200, 1 GiB frames (LZ4 text / Snappy log):
+    //   warp   (default) one warp per partition: LZ4 TMA-ring pipelined decoder 14.1 ms, Snappy 11.4 ms
+    //   ws     parser warp + lane-per-sequence copier warp per partition:        16-19 ms / 15.5 ms
+    //   bundle 32 lane-parsers + 16 copier warps per CTA:                        22 ms    / 18 ms
+    int decoder_mode = 1;
     bool lz4_frameless = false;
     bool batch_mode = false;        // last enqueue was a batch call (finish() returns -failures)
     int last_rc = 0;                // enqueue-time failure to report from finish()
@@ -118,7 +121,8 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_parts_ws_kernel, 64, 0);
     if (per_sm < 1) per_sm = 1;
     c->ws_blocks = per_sm * c->sm_count;
-    if (const char* e = getenv("AOCL_GPU_DECODER")) c->decoder_mode = strcmp(e, "warp") == 0 ? 1 : strcmp(e, "ws") == 0 ? 2 : 0;
+    if (const char* e = getenv("AOCL_GPU_DECODER"))
+        c->decoder_mode = strcmp(e, "ws") == 0 ? 2 : strcmp(e, "bundle") == 0 ? 3 : 1;
     *out = c;
     return 0;
 }
@@ -199,8 +203,13 @@ extern "C" int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t c, int32_t cod
     // for a range the capacity check applies to the range, not to the whole stream
     LLC_LAUNCH(rap_parse_kernel, 1, 1024, 0, c->stream, codec, (const uint8_t*)d_in, (uint64_t)n,
                ranged ? ~0ull : (uint64_t)out_cap, parts, c->d_res);
-    const bool warp_decoder = c->decoder_mode == 1 || (c->decoder_mode == 0 && codec == AOCL_GPU_LZ4);
-    if (warp_decoder)
+    const bool warp_decoder = c->decoder_mode == 1;
+    if (c->decoder_mode == 3) {
+        // the partition count is only known on the device here; size bundles for a 1 GiB-class frame
+        const uint32_t bundle = 28;
+        LLC_LAUNCH(decode_parts_bundle_kernel, c->sm_count, kBThreads, 0, c->stream, codec, (const uint8_t*)d_in,
+                   (uint8_t*)d_out, parts, c->d_res, first, count, out_origin, bundle);
+    } else if (warp_decoder)
         LLC_LAUNCH(decode_parts_kernel, c->decode_blocks, 128, 0, c->stream, codec, (const uint8_t*)d_in, (uint8_t*)d_out,
                    parts, c->d_res, first, count, out_origin);
     else
@@ -327,7 +336,7 @@ extern "C" int32_t aocl_gpu_decompress_batch_async(aocl_gpu_ctx_t c, int32_t cod
         c->last_rc = -2; return -2;
     }
     if (count) {
-        const bool warp_decoder = c->decoder_mode == 1 || (c->decoder_mode == 0 && codec == AOCL_GPU_LZ4);
+        const bool warp_decoder = c->decoder_mode != 2;
         if (warp_decoder) {
             const uint64_t blocks = (count + 3) / 4;
             const int grid = (int)(blocks < (uint64_t)c->decode_blocks * 4 ? blocks : (uint64_t)c->decode_blocks * 4);

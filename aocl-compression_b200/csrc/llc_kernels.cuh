@@ -6,6 +6,7 @@
 #include "snappy_codec.cuh"
 #include "lz4_decode_ring.cuh"
 #include "decode_wspec.cuh"
+#include "decode_bundle.cuh"
 
 namespace llc {
 
@@ -215,6 +216,52 @@ __global__ void __launch_bounds__(64, 24) decode_pages_ws_kernel(int codec, cons
         if (threadIdx.x == 0) {
             status[i] = got;
             if (got < 0) atomicAdd(&res->error, 1);
+        }
+        __syncthreads();
+    }
+}
+
+// Bundle variant (decode_bundle.cuh): one CTA = 32 lane-parsers + 16 copier warps; bundles of
+// `bundle` consecutive partitions are handed out through the atomic ticket.
+__global__ void __launch_bounds__(kBThreads, 1) decode_parts_bundle_kernel(int codec, const uint8_t* __restrict__ in, uint8_t* out,
+                                                                           const PartDesc* __restrict__ parts, CallResult* res,
+                                                                           uint32_t first, uint32_t count, uint64_t origin,
+                                                                           uint32_t bundle) {
+    __shared__ BShared sh;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (res->error) return;
+    const uint32_t T = (uint32_t)res->parts;
+    const uint32_t end = min(T, first + min(count, T));
+    for (;;) {
+        if (threadIdx.x == 0) sh.bundle = atomicAdd(&res->next, 1u);
+        __syncthreads();
+        const uint64_t base_i = (uint64_t)first + (uint64_t)sh.bundle * bundle;
+        if (base_i >= end) break;
+        if (threadIdx.x < kBSlots) {
+            BSlot& sl = sh.slot[threadIdx.x];
+            const uint64_t i = base_i + threadIdx.x;
+            sl.flags = 0; sl.tail = 0; sl.head = 0; sl.done = 0; sl.result = 0;
+            if (threadIdx.x < bundle && i < end) {
+                const PartDesc d = parts[i];
+                if (d.in_len != 0) {
+                    sl.in = in + d.in_off; sl.out = out + (d.out_off - origin);
+                    sl.clen = d.in_len; sl.cap = d.out_len;
+                    sl.flags = kBUsed | ((d.flags & kPartLast) ? kBLast : 0u) | ((d.flags & kPartExact) ? kBExact : 0u) |
+                               (codec != 0 ? kBSnappy : 0u);
+                }
+            }
+        }
+        __syncthreads();
+        if (warp == 0) bundle_parse(&sh, lane);
+        else bundle_copy(&sh, warp - 1, lane);
+        __syncthreads();
+        if (threadIdx.x < kBSlots) {
+            const BSlot& sl = sh.slot[threadIdx.x];
+            if (sl.flags & kBUsed) {
+                const long long got = sl.result;
+                if (got < 0 || ((sl.flags & kBExact) && (uint64_t)got != sl.cap)) atomicCAS(&res->error, 0, (int)(base_i + threadIdx.x) + 1);
+                else if (!(sl.flags & kBExact)) res->value = got;       // frame-less LZ4: size is whatever was produced
+            }
         }
         __syncthreads();
     }
