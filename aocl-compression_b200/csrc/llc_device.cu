@@ -36,6 +36,7 @@ struct aocl_gpu_ctx_s {
     // Measured on B200, 1 GiB text: 14 smem CTAs/SM = 100 ms, 14 smem + 16 gtab = 75 ms, 32 gtab = 54 ms.
     int gtab_ctas_per_sm = -1;      // AOCL_GPU_GTAB_CTAS: global-table CTAs per SM (-1 auto, 0 never)
     int stab_ctas_per_sm = -1;      // AOCL_GPU_STAB_CTAS: shared-table CTAs per SM (-1 auto, 0 never; max 14)
+    size_t l2_persist_bytes = 0, l2_window_bytes = 0;
     int snappy_gtab_ctas_per_sm = -1;   // AOCL_GPU_SNAPPY_GTAB_CTAS: Snappy global-table CTAs per SM (-1 auto, 0 never)
     int sm_count = 0;
     uint8_t* ws = nullptr;          // growable HBM workspace (scratch slots, tables, plans)
@@ -104,6 +105,17 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    // L2 persistence for the encoders' global hash tables (they are hit once per probe round)
+    {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        c->l2_persist_bytes = (size_t)max_persist;
+        c->l2_window_bytes = (size_t)max_window;
+        if (getenv("AOCL_GPU_NO_L2_PERSIST")) c->l2_persist_bytes = 0;
+        if (c->l2_persist_bytes) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_bytes);
+        if (getenv("AOCL_GPU_VERBOSE")) fprintf(stderr, "[aocl-llc-b200] L2 persisting max %d B, window max %d B\n", max_persist, max_window);
+    }
     if (const char* e = getenv("AOCL_GPU_GTAB_CTAS")) c->gtab_ctas_per_sm = atoi(e);
     if (const char* e = getenv("AOCL_GPU_SNAPPY_GTAB_CTAS")) c->snappy_gtab_ctas_per_sm = atoi(e);
     if (const char* e = getenv("AOCL_GPU_STAB_CTAS")) c->stab_ctas_per_sm = atoi(e) > 14 ? 14 : atoi(e);
@@ -274,6 +286,17 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
                 // fork: the global-table flavour shares the ticket and fills the idle warp slots
                 cudaEventRecord(c->ev_fork, c->stream);
                 cudaStreamWaitEvent(c->side, c->ev_fork, 0);
+                if (c->l2_persist_bytes) {                    // keep the hash tables resident in L2
+                    const size_t used = (size_t)(T < (uint32_t)g_ctas ? T : (uint32_t)g_ctas) * 16384;
+                    cudaStreamAttrValue av = {};
+                    av.accessPolicyWindow.base_ptr = tables;
+                    av.accessPolicyWindow.num_bytes = used < c->l2_window_bytes ? used : c->l2_window_bytes;
+                    const double ratio = (double)c->l2_persist_bytes / (double)av.accessPolicyWindow.num_bytes;
+                    av.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    cudaStreamSetAttribute(c->side, cudaStreamAttributeAccessPolicyWindow, &av);
+                }
                 lz4_encode_parts_gtab_kernel<<<(int)(T < (uint32_t)g_ctas ? T : (uint32_t)g_ctas), 32, 0, c->side>>>(
                     src, (uint64_t)n, T, scratch, slot, rec, ticket, tables);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -310,9 +333,24 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
         uint16_t* tables = reinterpret_cast<uint16_t*>(c->ws + o_tab);
         uint8_t* scratch = c->ws + o_scr;
         cudaMemsetAsync(ticket, 0, sizeof(uint32_t), c->stream);
+        if (F && g_grid && c->l2_persist_bytes) {              // keep the hash tables resident in L2
+            cudaStreamAttrValue av = {};
+            av.accessPolicyWindow.base_ptr = tables;
+            const size_t used = (size_t)g_grid * 32768;
+            av.accessPolicyWindow.num_bytes = used < c->l2_window_bytes ? used : c->l2_window_bytes;
+            const double ratio = (double)c->l2_persist_bytes / (double)av.accessPolicyWindow.num_bytes;
+            av.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        }
         if (F && g_grid) LLC_LAUNCH(snappy_encode_frags_gtab_kernel, g_grid, 32, 0, c->stream, src, g, scratch, slot, frag_len, ticket, tables);
         else if (F) LLC_LAUNCH(snappy_encode_frags_kernel, (F < (uint32_t)c->sm_count * 7u ? F : (uint32_t)c->sm_count * 7u), 32, 32768,
                                c->stream, src, g, scratch, slot, frag_len, ticket);
+        if (F && g_grid && c->l2_persist_bytes) {              // later kernels on this stream: no window
+            cudaStreamAttrValue av = {};
+            cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        }
         LLC_LAUNCH(snappy_plan_kernel, 1, 1024, 0, c->stream, g, frag_len, frag_off, dst, (uint64_t)out_cap, c->d_res);
         if (F) LLC_LAUNCH(snappy_compact_kernel, F, 256, 0, c->stream, scratch, slot, frag_len, frag_off, dst, c->d_res);
     }

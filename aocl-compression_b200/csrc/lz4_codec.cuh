@@ -411,15 +411,28 @@ __device__ inline uint32_t lz4_encode_warp_fused(const uint8_t* __restrict__ src
                 if (from_search && (int64_t)op + 1 + ll + 8 + ll / 255 > cap) { refused = true; break; }
                 if ((int64_t)op + 1 + ll_ext + ll + 2 + 6 + (code + 240) / 255 > cap) { refused = true; break; }
             }
-            if (lane == 0) dst[op] = (uint8_t)((min(ll, 15u) << 4) | min(code, 15u));
-            if (ll_ext) lz4_put_ext(dst + op + 1, ll - 15, lane);
-            if (ll <= 32) { if ((uint32_t)lane < ll) dst[op + 1 + ll_ext + lane] = src[anchor + lane]; }
-            else warp_copy(dst + op + 1 + ll_ext, src + anchor, ll, lane);
-            op += 1 + ll_ext + ll;
-            if (lane == 0) { dst[op] = (uint8_t)(ip - m); dst[op + 1] = (uint8_t)((ip - m) >> 8); }
-            op += 2;
-            if (ml_ext) lz4_put_ext(dst + op, code - 15, lane);
-            op += ml_ext;
+            if ((ll < 15u) & (code < 15u)) {
+                // whole sequence (token, <= 14 literals, offset) is at most 17 bytes: one byte per lane.
+                // In a post round lane j probed position anchor + j, so it already holds literal j.
+                const uint32_t offv = ip - m;
+                uint32_t v = __shfl_up_sync(kFull, cw.lo & 0xffu, 1);
+                if (!post && lane >= 1 && (uint32_t)lane <= ll) v = src[anchor + lane - 1];
+                if (lane == 0) v = (ll << 4) | code;
+                if ((uint32_t)lane == ll + 1u) v = offv & 0xffu;
+                if ((uint32_t)lane == ll + 2u) v = offv >> 8;
+                if ((uint32_t)lane <= ll + 2u) dst[op + lane] = (uint8_t)v;
+                op += ll + 3u;
+            } else {
+                if (lane == 0) dst[op] = (uint8_t)((min(ll, 15u) << 4) | min(code, 15u));
+                if (ll_ext) lz4_put_ext(dst + op + 1, ll - 15, lane);
+                if (ll <= 32) { if ((uint32_t)lane < ll) dst[op + 1 + ll_ext + lane] = src[anchor + lane]; }
+                else warp_copy(dst + op + 1 + ll_ext, src + anchor, ll, lane);
+                op += 1 + ll_ext + ll;
+                if (lane == 0) { dst[op] = (uint8_t)(ip - m); dst[op + 1] = (uint8_t)((ip - m) >> 8); }
+                op += 2;
+                if (ml_ext) lz4_put_ext(dst + op, code - 15, lane);
+                op += ml_ext;
+            }
 
             base = mpos + 4 + mc;                           // first position after the match
             anchor = base;

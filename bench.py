@@ -74,11 +74,24 @@ class RefDesc(C.Structure):
                 ("optOff", C.c_int), ("optLevel", C.c_int)]
 
 
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def load_reference():
     path = os.path.join(ROOT, "oracle", "_ref", "libaocl_ref.so")
     if not os.path.exists(path):
         return None
     L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm must use every host core
+    try:
+        omp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
+        omp.omp_set_num_threads(host_threads())
+    except OSError:
+        pass
     dp = C.POINTER(RefDesc)
     L.aocl_llc_setup.restype, L.aocl_llc_setup.argtypes = C.c_int32, [dp, C.c_int]
     L.aocl_llc_compress.restype, L.aocl_llc_compress.argtypes = C.c_int64, [dp, C.c_int]
@@ -123,7 +136,7 @@ def run_reference(args, wl):
     if L is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libaocl_ref.so not built"}))
         return
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     sample = min(wl["size"], args.ref_sample)
     data = make_data(wl["gen"], sample, wl["seed"])
     per, tc, td, csize = reference_round_trip(L, data, wl["codec"], args.steps, args.warmup)
@@ -144,6 +157,7 @@ def run_reference(args, wl):
 
 # ------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """nvidia-smi in loop mode (100 ms) for the duration of the timed region."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -151,31 +165,38 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.rows = []
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.proc = None
 
     def __enter__(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            time.sleep(0.15)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.splitlines():
+            self.rows.append([x.strip() for x in line.split(",")])
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[1]) for r in self.rows if len(r) >= 9 and num(r[1]) is not None]
+        mx = [num(r[2]) for r in self.rows if len(r) >= 9 and num(r[2]) is not None]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -327,7 +348,7 @@ def run_b200(args, wl):
         if R is not None:
             sample = min(U, args.ref_sample)
             per, rtc, rtd, rcs = reference_round_trip(R, data[:sample], codec, 2, 1)
-            cores = os.cpu_count() or 1
+            cores = host_threads()
             cpu_baseline = {"value": 2 * sample / per / 1e9, "unit": "GB/s", "cores": cores, "kind": "reference",
                             "sample": f"first {sample >> 20} MiB of the workload, OpenMP max threads = {cores}",
                             "compress_GBps": sample / rtc / 1e9, "decompress_GBps": sample / rtd / 1e9}
