@@ -1,0 +1,714 @@
+// decode_tile.cuh -- tile decoder: one 512-thread CTA per unit (RAP partition or page), LANE PER
+// SEQUENCE, with the last 64 KiB of output kept in a shared-memory ring.
+//
+// Why.  A unit is one serial token chain, and the warp-per-unit decoders (lz4_decode_ring.cuh) spend
+// ~160 warp instructions per 10-byte sequence: the whole GPU ends up issue bound at ~1 % of the HBM
+// roofline.  Byte-granular copies against global memory cost one L1 wavefront per lane, so handing
+// sequences to lanes only pays if the bytes live in shared memory.  Here:
+//
+//   * the compressed stream arrives in 4 KiB chunks through the TMA bulk-copy engine
+//     (cp.async.bulk + mbarrier, double buffered);
+//   * PARSE is data parallel: every byte position of the chunk is treated as a potential token and
+//     gets a "next token" link (n1); four rounds of pointer doubling give 16-hop links; one thread
+//     chases the 16-hop links from the known chunk entry (<= 86 dependent shared loads per chunk)
+//     and 8-hop/1-hop links expand the anchors into the list of real sequence starts;
+//   * a block scan of the sequence lengths gives every sequence its output position; offsets and
+//     capacity are validated there (the first irregular sequence truncates the group);
+//   * COPY is lane per sequence inside shared memory: literals chunk -> ring, matches ring -> ring
+//     in dependency rounds (a match waits for the sequences its source overlaps, tracked in a
+//     bitmap; sources older than the group are always final);
+//   * the finished span is flushed ring -> HBM with aligned 16-byte stores, so HBM only sees
+//     coalesced traffic: C bytes in through TMA, U bytes out through STG.128.
+//
+// Anything irregular -- length runs >= 270 (a 255 extension byte), the last ~300 bytes of a stream,
+// sequences that would cross the output capacity, malformed input -- is executed one sequence at a
+// time by the fully checked slow step, which mirrors lz4_slow_sequence()/snappy_decode_warp() and
+// through them the reference decoders (algos/lz4/lz4.c:3806-4305; algos/snappy/snappy.cc:1466-1570,
+// 2185-2199).  Accept/reject behaviour and produced bytes are identical to the warp decoders.
+#pragma once
+#include "in_ring.cuh"
+#include "snappy_codec.cuh"
+
+namespace llc {
+
+constexpr int kTThreads = 512;
+constexpr int kTWarps = kTThreads / 32;
+constexpr uint32_t kTRingMask = 65535u;
+constexpr uint32_t kTChunkLog = 12, kTChunk = 1u << kTChunkLog;
+constexpr uint32_t kTMargin = 384;                       // a regular sequence reads < 280 bytes past its token
+constexpr uint32_t kTBuf = kTChunk + kTMargin;           // multiple of 16
+constexpr uint32_t kTSpan = 16384;                       // output bytes per group (truncated beyond)
+constexpr uint32_t kTSpanBlocks = kTSpan / 32 + 32;
+constexpr uint32_t kTFastTail = 300;                     // tokens this close to the stream end take the slow step
+constexpr uint32_t kTPiece = 16384;                      // slow-step copy granule
+constexpr uint32_t kTNone = 0xffffu;
+constexpr uint32_t kTCapMax = 0xffffff00u;
+
+template <class Fmt>
+struct TileShared {
+    static constexpr int MAXSEQ = Fmt::kMaxSeq;
+    alignas(128) uint8_t ring[65536];
+    alignas(128) uint8_t inbuf[2][kTBuf];
+    uint16_t n1[kTChunk], ta[kTChunk], tb[kTChunk];
+    uint32_t src[MAXSEQ];                                // current source position of each match (redirected)
+    uint16_t dl[MAXSEQ + 32];                            // output position of each sequence relative to the group (+ end)
+    uint16_t seq_start[MAXSEQ];
+    uint16_t llen[MAXSEQ];                               // literal length; bit 15: its match part cannot be redirected into
+    uint16_t blk2seq[kTSpanBlocks];                      // sequence covering byte 32*B of the group span
+    uint32_t done_bits[MAXSEQ / 32 + 1];
+    uint32_t batch_tot[MAXSEQ / 32 + 1];
+    uint16_t anchors[MAXSEQ / 64 + 2];                   // 64-sequence anchors
+    uint16_t anchors8[8];                                // then up to seven 8-sequence anchors
+    uint16_t tail[8];                                    // then up to seven single sequences
+    alignas(8) uint64_t bar[2];
+    uint32_t nanch, nanch8, ntail, end_kind, end_pos, first_bad, unit, abort;
+};
+
+struct TSeq { uint32_t nxt, lit, ll, ml, off; };         // chunk-relative indices; nxt == kTNone: irregular
+
+// Per-unit decoder state.  Everything is uniform across the CTA (kept redundantly in registers).
+struct TileState {
+    const uint8_t* gin;      // 16-byte aligned, <= first stream byte
+    uint8_t* gout;           // 16-byte aligned, <= first output byte; positions below are relative to it
+    uint32_t iend;           // stream end (relative to gin)
+    uint32_t a;              // first output position (out & 15)
+    uint32_t cap;            // output end (a + capacity)
+    uint32_t ip, op, flushed;
+    uint32_t par;            // mbarrier parities (bit b = next phase of buffer b); persists across units
+    uint32_t pend;           // bit b: a load into buffer b is in flight
+    int32_t bufc[2];         // chunk held by / in flight into each buffer
+    int32_t tabc;            // chunk the link tables describe
+    bool last;
+};
+
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(kFull, v); }
+
+// Debug counters (AOCL_GPU tile decoder bring-up): [0..15] cycles per phase summed over CTAs (thread 0),
+// [16..23] event counts, [24..31] watchdog codes.  Compiled in only with -DLLC_TILE_PROF.
+__device__ unsigned long long g_tile_prof[32];
+#ifdef LLC_TILE_PROF
+#define TP_DECL long long tp_t0 = clock64();
+#define TP(i) do { if (threadIdx.x == 0) { const long long tp_t1 = clock64(); atomicAdd(&g_tile_prof[i], (unsigned long long)(tp_t1 - tp_t0)); tp_t0 = tp_t1; } } while (0)
+#define TC(i, v) do { if (threadIdx.x == 0) atomicAdd(&g_tile_prof[16 + (i)], (unsigned long long)(v)); } while (0)
+#else
+#define TP_DECL
+#define TP(i) do {} while (0)
+#define TC(i, v) do {} while (0)
+#endif
+#define TWATCH(code) do { atomicAdd(&g_tile_prof[24 + (code)], 1ull); } while (0)
+constexpr uint32_t kTSpinMax = 1u << 22;
+
+// 8 bytes starting at byte index idx of a 4-byte aligned shared array (word index wrapped with wmask)
+__device__ __forceinline__ void lds_unaligned8(const uint32_t* w32, uint32_t idx, uint32_t wmask, uint32_t& lo, uint32_t& hi) {
+    const uint32_t wi = idx >> 2, sh = (idx & 3u) * 8u;
+    const uint32_t w0 = w32[wi & wmask], w1 = w32[(wi + 1u) & wmask], w2 = w32[(wi + 2u) & wmask];
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+// the low min(n, 8) bytes of (lo, hi) to ring positions pos, pos+1, ...
+__device__ __forceinline__ void sts_bytes8(uint8_t* ring, uint32_t pos, uint32_t lo, uint32_t hi, uint32_t n) {
+#pragma unroll
+    for (uint32_t j = 0; j < 8; j++)
+        if (j < n) ring[(pos + j) & 65535u] = (uint8_t)((j < 4 ? lo : hi) >> (8u * (j & 3u)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Formats
+// ------------------------------------------------------------------------------------------------
+struct TileLz4 {
+    static constexpr int kMaxSeq = 1024;                 // sequences per group (a 4 KiB chunk of text holds ~700)
+    static constexpr bool kHasLit = true;                // a sequence carries literals and a match
+    static constexpr uint32_t kEndSlack = 12;            // regular sequences end >= 12 bytes before the capacity
+
+    __device__ static __forceinline__ TSeq parse(const uint8_t* bp, uint32_t i) {
+        TSeq s;
+        const uint32_t tok = bp[i], e1 = bp[i + 1];
+        const uint32_t nibL = tok >> 4, nibM = tok & 15u;
+        const bool extL = nibL == 15u, extM = nibM == 15u;
+        s.ll = nibL + (extL ? e1 : 0u);
+        s.lit = i + 1u + (extL ? 1u : 0u);
+        const uint32_t q = s.lit + s.ll;
+        s.off = (uint32_t)bp[q] | ((uint32_t)bp[q + 1] << 8);
+        const uint32_t e2 = bp[q + 2];
+        s.ml = 4u + nibM + (extM ? e2 : 0u);
+        const bool special = (extL && e1 == 255u) || (extM && e2 == 255u);
+        s.nxt = special ? kTNone : q + 2u + (extM ? 1u : 0u);
+        return s;
+    }
+};
+
+struct TileSnappy {
+    static constexpr int kMaxSeq = 1408;                 // elements per group (a 4 KiB chunk of text holds ~1200)
+    static constexpr bool kHasLit = false;               // an element is either literals or a copy
+    static constexpr uint32_t kEndSlack = 0;
+
+    // one element = one "sequence" with either literals or a copy
+    __device__ static __forceinline__ TSeq parse(const uint8_t* bp, uint32_t i) {
+        TSeq s;
+        const uint32_t tag = bp[i], b1 = bp[i + 1], b2 = bp[i + 2];
+        const uint32_t kind = tag & 3u;
+        s.ll = 0; s.ml = 0; s.off = 0; s.lit = i + 1u; s.nxt = kTNone;
+        if (kind == 0) {
+            const uint32_t v = tag >> 2;
+            if (v < 60u) { s.ll = v + 1u; s.nxt = i + 1u + s.ll; }
+            else if (v == 60u) { s.ll = b1 + 1u; s.lit = i + 2u; s.nxt = i + 2u + s.ll; }
+        } else if (kind == 1) {
+            s.ml = 4u + ((tag >> 2) & 7u); s.off = ((tag >> 5) << 8) | b1; s.nxt = i + 2u;
+        } else if (kind == 2) {
+            s.ml = 1u + (tag >> 2); s.off = b1 | (b2 << 8); s.nxt = i + 3u;
+        }
+        return s;
+    }
+};
+
+static_assert(sizeof(TileShared<TileLz4>) <= 115712 && sizeof(TileShared<TileSnappy>) <= 115712,
+              "two CTAs per SM need <= 113 KiB of shared memory each");
+
+// ------------------------------------------------------------------------------------------------
+// Ring -> HBM.  Writes [st.flushed, hi) with aligned 16-byte stores; a partial first unit is written
+// byte-wise, a partial last unit only when `final` (otherwise it stays in the ring for the next flush).
+// ------------------------------------------------------------------------------------------------
+template <class Fmt>
+__device__ __forceinline__ void tile_flush(TileShared<Fmt>& sh, TileState& st, uint32_t hi, bool final) {
+    uint32_t lo = st.flushed;
+    const uint32_t tid = threadIdx.x;
+    if (lo >= hi) return;
+    if (lo & 15u) {
+        const uint32_t n = min((lo + 15u) & ~15u, hi) - lo;
+        if (tid < n) st.gout[lo + tid] = sh.ring[(lo + tid) & kTRingMask];
+        lo += n;
+    }
+    const uint32_t hi_al = hi & ~15u;
+    if (!(lo & 15u) && hi_al > lo) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(sh.ring);
+        uint4* g4 = reinterpret_cast<uint4*>(st.gout);
+        for (uint32_t u = (lo >> 4) + tid; u < (hi_al >> 4); u += kTThreads) g4[u] = r4[u & (kTRingMask >> 4)];
+        lo = hi_al;
+    }
+    if (final && hi > lo) {
+        if (tid < hi - lo) st.gout[lo + tid] = sh.ring[(lo + tid) & kTRingMask];
+        lo = hi;
+    }
+    st.flushed = lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Slow step helpers: CTA-cooperative copies through the ring, flushed piece by piece.
+// ------------------------------------------------------------------------------------------------
+template <class Fmt>
+__device__ __forceinline__ void tile_slow_literals(TileShared<Fmt>& sh, TileState& st, uint32_t p, uint32_t ll) {
+    for (uint32_t done = 0; done < ll; done += kTPiece) {
+        const uint32_t n = min(kTPiece, ll - done);
+        const uint32_t d = st.op + done;
+        for (uint32_t j = threadIdx.x; j < n; j += kTThreads) sh.ring[(d + j) & kTRingMask] = st.gin[p + done + j];
+        __syncthreads();
+        tile_flush(sh, st, d + n, false);
+    }
+    st.op += ll;
+}
+// out[op .. op+ml) = out[op-off ..]; a match that overlaps itself is periodic with period `off`.
+template <class Fmt>
+__device__ __forceinline__ void tile_slow_match(TileShared<Fmt>& sh, TileState& st, uint32_t off, uint32_t ml) {
+    const uint32_t s = st.op - off;
+    const bool periodic = off < ml;
+    for (uint32_t done = 0; done < ml; done += kTPiece) {
+        const uint32_t n = min(kTPiece, ml - done);
+        const uint32_t d = st.op + done;
+        const uint32_t hi = d + n;
+        const uint32_t ring_lo = hi > 65536u ? hi - 65536u : 0u;      // older bytes have left the ring (they are flushed)
+        for (uint32_t j = threadIdx.x; j < n; j += kTThreads) {
+            const uint32_t k = done + j;
+            const uint32_t sp = s + (periodic ? k % off : k);
+            const uint8_t v = sp < ring_lo ? st.gout[sp] : sh.ring[sp & kTRingMask];
+            sh.ring[(d + j) & kTRingMask] = v;
+        }
+        __syncthreads();
+        tile_flush(sh, st, hi, false);
+        __syncthreads();                                             // flushed bytes may be read back by the next piece
+    }
+    st.op += ml;
+}
+
+// One fully checked LZ4 sequence at st.ip (mirrors lz4_slow_sequence, lz4_decode_ring.cuh).
+// Returns 0: continue, 1: stream finished, -1: corrupt.  Uniform across the CTA.
+template <class Fmt>
+__device__ __forceinline__ int tile_slow_step_lz4(TileShared<Fmt>& sh, TileState& st) {
+    const uint8_t* in = st.gin;
+    const uint32_t iend = st.iend, cap = st.cap;
+    uint32_t ip = st.ip;
+    if (ip >= iend) return -1;
+    const uint32_t tok = in[ip];
+    uint32_t ll = tok >> 4, p = ip + 1;
+    if (ll == 15) {
+        uint32_t b;
+        do {
+            if (p >= iend) return -1;
+            b = in[p++]; ll += b;
+        } while (b == 255 && ll < 0x7fff0000u);
+    }
+    if (ll > iend - p || ll > cap - st.op) return -1;
+    // end-of-block parsing restrictions, lz4.c:4104-4164
+    const bool closing = ((uint64_t)st.op + ll + 12 > cap) || ((uint64_t)p + ll + 8 > iend);
+    if (closing && st.last && p + ll != iend) return -1;
+    tile_slow_literals(sh, st, p, ll);
+    const uint32_t q = p + ll;
+    st.ip = q;
+    if (closing && (st.last || st.op == cap)) return 1;
+    if (q == iend) return 1;
+    if (q + 2 > iend) return -1;
+    const uint32_t off = (uint32_t)in[q] | ((uint32_t)in[q + 1] << 8);
+    ip = q + 2;
+    uint32_t ml = tok & 15;
+    if (ml == 15) {
+        uint32_t b;
+        do {
+            if (ip >= iend) return -1;
+            b = in[ip++]; ml += b;
+        } while (b == 255 && ml < 0x7fff0000u);
+    }
+    ml += 4;
+    st.ip = ip;
+    if (off == 0 || off > st.op - st.a) return -1;                   // lz4.c:4196-4197
+    if (ml > cap - st.op) return -1;
+    if (st.last && (uint64_t)st.op + ml + 5 > cap) return -1;        // lz4.c:4262-4264
+    tile_slow_match(sh, st, off, ml);
+    if (!st.last && (st.op == cap || ip >= iend)) return 1;          // lz4.c:4285-4288
+    return 0;
+}
+
+// One fully checked Snappy element at st.ip (mirrors snappy_decode_warp, snappy_codec.cuh).
+template <class Fmt>
+__device__ __forceinline__ int tile_slow_step_snappy(TileShared<Fmt>& sh, TileState& st) {
+    const uint8_t* in = st.gin;
+    const uint32_t iend = st.iend, cap = st.cap;
+    uint32_t ip = st.ip;
+    if (ip >= iend) return st.op == cap ? 1 : -1;                    // snappy.cc:1715
+    const uint32_t tag = in[ip++];
+    uint32_t len, off;
+    if ((tag & 3) == 0) {                                            // literal, snappy.cc:1492-1527
+        len = (tag >> 2) + 1;
+        if (len > 60) {
+            const uint32_t nb = len - 60;
+            if (ip + nb > iend) return -1;
+            uint32_t v = 0;
+            for (uint32_t k = 0; k < nb; k++) v |= (uint32_t)in[ip + k] << (8 * k);
+            ip += nb;
+            if (v == 0xffffffffu) return -1;
+            len = v + 1;
+        }
+        if (len > iend - ip || len > cap - st.op) return -1;
+        tile_slow_literals(sh, st, ip, len);
+        st.ip = ip + len;
+        return 0;
+    }
+    const uint32_t kind = tag & 3;                                   // char_table, snappy-internal.h:406-439
+    if (kind == 1) {
+        if (ip + 1 > iend) return -1;
+        len = 4 + ((tag >> 2) & 7); off = ((tag >> 5) << 8) | in[ip]; ip += 1;
+    } else if (kind == 2) {
+        if (ip + 2 > iend) return -1;
+        len = 1 + (tag >> 2); off = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8); ip += 2;
+    } else {
+        if (ip + 4 > iend) return -1;
+        len = 1 + (tag >> 2); off = ld_u32_bytes(in + ip); ip += 4;
+    }
+    st.ip = ip;
+    if (off == 0 || off > st.op - st.a || len > cap - st.op) return -1;     // snappy.cc:2185-2199
+    tile_slow_match(sh, st, off, len);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Input chunks (TMA bulk copies, double buffered)
+// ------------------------------------------------------------------------------------------------
+template <class Fmt>
+__device__ __forceinline__ void tile_wait_buf(TileShared<Fmt>& sh, TileState& st, int b) {
+    if (st.pend & (1u << b)) {
+        uint32_t spins = 0;
+        while (!mbar_try_wait(&sh.bar[b], (st.par >> b) & 1u)) {
+            if (++spins > kTSpinMax) { TWATCH(0); sh.abort = 1; break; }
+        }
+        st.par ^= 1u << b;
+        st.pend &= ~(1u << b);
+    }
+}
+// Caller guarantees (with a __syncthreads) that nobody still reads buffer b.
+template <class Fmt>
+__device__ __forceinline__ void tile_issue_buf(TileShared<Fmt>& sh, TileState& st, int b, int32_t chunk) {
+    tile_wait_buf(sh, st, b);                                        // at most one load per buffer in flight
+    const uint32_t base = (uint32_t)chunk << kTChunkLog;
+    st.bufc[b] = chunk;
+    if (base >= st.iend) return;
+    const uint32_t left = st.iend - base;
+    const uint32_t bytes = left >= kTBuf ? kTBuf : ((left + 15u) & ~15u);
+    if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&sh.bar[b], bytes);
+        bulk_g2s(sh.inbuf[b], st.gin + base, bytes, &sh.bar[b]);
+    }
+    st.pend |= 1u << b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One group: the regular sequences that start in the current chunk, from st.ip up to the first
+// irregular one.  Returns 1 when a slow step has to follow at st.ip, 0 when not, -1 on a watchdog abort.
+// ------------------------------------------------------------------------------------------------
+template <class Fmt>
+__device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, uint32_t fast_i_ex) {
+    constexpr int MAXSEQ = Fmt::kMaxSeq;
+    constexpr int kRounds = (MAXSEQ / 32 + kTWarps - 1) / kTWarps;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const int32_t chunk = (int32_t)(st.ip >> kTChunkLog);
+    const int b = chunk & 1;
+    const uint32_t cbase = (uint32_t)chunk << kTChunkLog;
+    const uint8_t* bp = sh.inbuf[b];
+
+    TP_DECL
+    __syncthreads();                                                 // previous phase is done with both buffers
+    if (st.bufc[b] != chunk) tile_issue_buf(sh, st, b, chunk);
+    if (st.bufc[b ^ 1] != chunk + 1 && cbase + kTChunk < st.iend) tile_issue_buf(sh, st, b ^ 1, chunk + 1);
+    tile_wait_buf(sh, st, b);
+    TP(0);
+
+    // ---- links: n1 = next token; 2/4/8-hop links by pointer doubling (n8 ends up in ta); n64 = n8 applied
+    //      eight times (tb).  Every thread owns 8 positions; loads are issued together, stores afterwards.
+    if (st.tabc != chunk) {
+        constexpr int kPer = kTChunk / kTThreads;
+        uint32_t v[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            const uint32_t i = tid + j * kTThreads;
+            v[j] = (cbase + i < fast_i_ex) ? Fmt::parse(bp, i).nxt : kTNone;
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; j++) sh.n1[tid + j * kTThreads] = (uint16_t)v[j];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.n1[v[j]];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) sh.ta[tid + j * kTThreads] = (uint16_t)v[j];                  // n2
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.ta[v[j]];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) sh.tb[tid + j * kTThreads] = (uint16_t)v[j];                  // n4
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.tb[v[j]];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) sh.ta[tid + j * kTThreads] = (uint16_t)v[j];                  // n8
+        __syncthreads();
+#pragma unroll
+        for (int h = 1; h < 8; h++) {
+#pragma unroll
+            for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.ta[v[j]];
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; j++) sh.tb[tid + j * kTThreads] = (uint16_t)v[j];                  // n64
+        st.tabc = chunk;
+        __syncthreads();
+        TC(0, 1);
+    }
+    TP(1);
+
+    // ---- chase: 64-sequence anchors, then 8-sequence anchors, then single steps up to the chunk exit or
+    //      the first irregular token
+    if (tid == 0) {
+        uint32_t p = st.ip - cbase, na = 0, na8 = 0, nt = 0, kind = 0;   // kind 0: left the chunk, 1: irregular token at p
+        uint32_t n;
+        while (p < kTChunk && na < MAXSEQ / 64 - 2 && (n = sh.tb[p]) != kTNone) { sh.anchors[na++] = (uint16_t)p; p = n; }
+        while (p < kTChunk && na8 < 7 && (n = sh.ta[p]) != kTNone) { sh.anchors8[na8++] = (uint16_t)p; p = n; }
+        while (p < kTChunk && nt < 7) {
+            n = sh.n1[p];
+            if (n == kTNone) { kind = 1; break; }
+            sh.tail[nt++] = (uint16_t)p;
+            p = n;
+        }
+        sh.nanch = na; sh.nanch8 = na8; sh.ntail = nt; sh.end_kind = kind; sh.end_pos = p;
+        sh.first_bad = 0xffffffffu;
+    }
+    if (tid < MAXSEQ / 32 + 1) sh.done_bits[tid] = 0;
+    __syncthreads();
+    const uint32_t nanch = sh.nanch, ntail = sh.ntail;
+    const uint32_t n8a = nanch * 8u + sh.nanch8;                     // 8-sequence runs
+    const uint32_t nseq = n8a * 8u + ntail;
+    const uint32_t end_ip = cbase + sh.end_pos;
+    const bool end_special = sh.end_kind != 0;
+    TP(2);
+    TC(1, 1); TC(2, nseq);
+    if (sh.abort) return -1;
+    if (nseq == 0) { st.ip = end_ip; return 1; }                     // irregular token right at st.ip
+
+    // ---- expand into sequence starts: one thread per 8-sequence run
+    if (tid < n8a) {
+        uint32_t p;
+        if (tid < nanch * 8u) {
+            p = sh.anchors[tid >> 3];
+            for (uint32_t h = tid & 7u; h; h--) p = sh.ta[p];
+        } else p = sh.anchors8[tid - nanch * 8u];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { sh.seq_start[tid * 8u + j] = (uint16_t)p; p = sh.n1[p]; }
+    }
+    if (tid < ntail) sh.seq_start[n8a * 8u + tid] = sh.tail[tid];
+    __syncthreads();
+    TP(3);
+
+    // ---- fields + lengths, scanned to output positions
+    const uint32_t nbatch = (nseq + 31u) >> 5;
+    uint32_t f_len[kRounds], f_src[kRounds], f_dl[kRounds];          // ll | ml<<16, off | lit<<16, output position
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+        const uint32_t bt = warp + r * kTWarps, k = bt * 32u + lane;
+        uint32_t ll = 0, ml = 0, off = 0, lit = 0;
+        if (k < nseq) { const TSeq s = Fmt::parse(bp, sh.seq_start[k]); ll = s.ll; ml = s.ml; off = s.off; lit = s.lit; }
+        const uint32_t len = ll + ml;
+        const uint32_t incl = warp_incl_sum(len, lane);
+        f_len[r] = ll | (ml << 16); f_src[r] = off | (lit << 16); f_dl[r] = incl - len;
+        if (lane == 31 && bt < nbatch) sh.batch_tot[bt] = incl;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t v0 = lane < nbatch ? sh.batch_tot[lane] : 0u;
+        const uint32_t v1 = lane + 32u < nbatch ? sh.batch_tot[lane + 32] : 0u;
+        const uint32_t s0 = warp_incl_sum(v0, lane);
+        const uint32_t t0 = __shfl_sync(kFull, s0, 31);
+        const uint32_t s1 = warp_incl_sum(v1, lane) + t0;
+        if (lane < nbatch) sh.batch_tot[lane] = s0 - v0;
+        if (lane + 32u < nbatch) sh.batch_tot[lane + 32] = s1 - v1;
+    }
+    __syncthreads();
+    const uint32_t op0 = st.op;
+    const uint32_t lim_o = st.cap >= op0 + Fmt::kEndSlack ? min(st.cap - Fmt::kEndSlack, op0 + kTSpan) : 0u;
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+        const uint32_t bt = warp + r * kTWarps, k = bt * 32u + lane;
+        if (k < nseq) {
+            const uint32_t ll = f_len[r] & 0xffffu, ml = f_len[r] >> 16, off = f_src[r] & 0xffffu;
+            const uint32_t dlk = op0 + sh.batch_tot[bt] + f_dl[r];
+            const uint32_t dm = dlk + ll, end = dm + ml;
+            f_dl[r] = dlk;
+            sh.dl[k] = (uint16_t)(dlk - op0);
+            sh.llen[k] = (uint16_t)(ll | ((ml == 0 || off < ml) ? 0x8000u : 0u));
+            sh.src[k] = dm - off;
+            if (k == nseq - 1) sh.dl[nseq] = (uint16_t)(end - op0);
+            const bool bad = (ml != 0 && (off == 0 || off > dm - st.a)) || end > lim_o;
+            if (bad) atomicMin(&sh.first_bad, k);
+            for (uint32_t B = (dlk - op0 + 31u) >> 5; (B << 5) < end - op0 && B < kTSpanBlocks; B++) sh.blk2seq[B] = (uint16_t)k;
+        }
+        if (!Fmt::kHasLit) {                                         // pure-literal elements never have to be waited for
+            const unsigned z = __ballot_sync(kFull, k < nseq && (f_len[r] >> 16) == 0);
+            if (lane == 0 && z) atomicOr(&sh.done_bits[bt], z);
+        }
+    }
+    __syncthreads();
+    TP(4);
+    const uint32_t nexec = min(nseq, sh.first_bad);
+    TC(3, nexec);
+    if (nexec == 0) return 1;                                        // first sequence is irregular: slow step at st.ip
+    const uint32_t g_hi = op0 + sh.dl[nexec];
+    const uint32_t ring_lo = g_hi > 65536u ? g_hi - 65536u : 0u;
+
+    // ---- literals: chunk buffer -> ring, one lane per sequence (runs > 32 bytes by the whole warp)
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+        const uint32_t bt = warp + r * kTWarps, k = bt * 32u + lane;
+        if (bt * 32u >= nexec) break;
+        const bool act = k < nexec;
+        const uint32_t ll = act ? (f_len[r] & 0xffffu) : 0u, lit = f_src[r] >> 16, dlk = f_dl[r];
+        const uint32_t n = ll <= 32u ? ll : 0u;
+        const uint32_t mx = warp_max_u32(n);
+        for (uint32_t t = 0; t < mx; t += 8) {
+            if (t < n) {
+                uint32_t lo, hi;
+                lds_unaligned8(reinterpret_cast<const uint32_t*>(bp), lit + t, 0xffffffffu, lo, hi);
+                sts_bytes8(sh.ring, dlk + t, lo, hi, n - t);
+            }
+        }
+        unsigned big = __ballot_sync(kFull, ll > 32u);
+        while (big) {
+            const int l = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t src = __shfl_sync(kFull, lit, l), d = __shfl_sync(kFull, dlk, l), len = __shfl_sync(kFull, ll, l);
+            for (uint32_t j = lane; j < len; j += 32) sh.ring[(d + j) & kTRingMask] = bp[src + j];
+        }
+    }
+    TP(5);
+
+    // ---- source forwarding.  Text-like data chains every occurrence of a string to the previous one, so
+    //      the dependency graph of a group is hundreds of levels deep.  A match whose source lies entirely
+    //      inside the destination of an earlier match j of the group can read from j's source instead
+    //      (same bytes, older position); iterating this is pointer doubling on the chain and leaves only
+    //      the partially overlapping links as real dependencies.  Self-overlapping matches take no part.
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+        const uint32_t bt = warp + r * kTWarps, k = bt * 32u + lane;
+        if (bt * 32u >= nexec) break;
+        const uint32_t ll = f_len[r] & 0xffffu, ml = f_len[r] >> 16, off = f_src[r] & 0xffffu;
+        const uint32_t dm = f_dl[r] + ll;
+        uint32_t sp = dm - off;
+        bool act = k < nexec && ml != 0 && off >= ml;
+        for (int it = 0; it < 12; it++) {
+            bool moved = false;
+            if (act && sp >= op0) {
+                const uint32_t x = sp - op0;
+                uint32_t j = sh.blk2seq[x >> 5];
+                while (j < k && sh.dl[j + 1] <= x) j++;
+                const uint32_t lj = sh.llen[j];
+                const uint32_t dmj = (uint32_t)sh.dl[j] + (lj & 0x7fffu);
+                if (j < k && !(lj & 0x8000u) && x >= dmj && x + ml <= sh.dl[j + 1]) {
+                    const uint32_t cand = ((volatile uint32_t*)sh.src)[j] + (x - dmj);
+                    if (cand >= ring_lo) { sp = cand; sh.src[k] = cand; moved = true; } else act = false;
+                } else act = false;
+            } else act = false;
+            if (!__any_sync(kFull, moved)) break;
+        }
+        f_src[r] = (f_src[r] & 0xffff0000u) | 0u;                    // offset no longer needed
+        f_dl[r] = dm;                                                // match destination
+        f_len[r] = ml | ((off < ml ? off : 0u) << 16);               // ml | period << 16
+        // keep the forwarded source in place of (off | lit)
+        f_src[r] = sp;
+    }
+    __syncthreads();                                                 // every literal of the group is in the ring
+    TP(9);
+
+    // ---- matches: ring -> ring in dependency rounds
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+        const uint32_t bt = warp + r * kTWarps, k = bt * 32u + lane;
+        if (bt * 32u >= nexec) break;
+        const uint32_t ml = f_len[r] & 0xffffu, period = f_len[r] >> 16;
+        const uint32_t dm = f_dl[r];
+        const uint32_t s = f_src[r];
+        bool pending = k < nexec && ml != 0;
+        int jlo = 1, jhi = 0;
+        if (pending) {
+            const uint32_t e = min(s + ml, dm);                      // source bytes that precede the destination
+            if (e > op0) {
+                const uint32_t x = max(s, op0) - op0, y = e - 1u - op0;
+                uint32_t j = sh.blk2seq[x >> 5];
+#ifdef LLC_TILE_PROF
+                if (j > k || sh.dl[j] > x) TWATCH(2);
+#endif
+                while (j < k && sh.dl[j + 1] <= x) j++;
+                jlo = (int)j;
+                while (j < k && sh.dl[j + 1] <= y) j++;
+                if (j >= k) jhi = (int)k - 1;                        // own literals are already in place
+                else if (y < (uint32_t)sh.dl[j] + (sh.llen[j] & 0x7fffu)) jhi = (int)j - 1;   // ends inside j's literals
+                else jhi = (int)j;
+            }
+        }
+        const bool far = s < ring_lo;
+        unsigned left = __ballot_sync(kFull, pending);
+        uint32_t spins = 0;
+        while (left) {
+            bool ready = pending;
+            if (ready && jlo <= jhi) {
+                const volatile uint32_t* db = sh.done_bits;
+                for (int w = jlo >> 5; w <= (jhi >> 5); w++) {
+                    const uint32_t lo_bit = (w == (jlo >> 5)) ? (uint32_t)(jlo & 31) : 0u;
+                    const uint32_t hi_bit = (w == (jhi >> 5)) ? (uint32_t)(jhi & 31) : 31u;
+                    const uint32_t mask = (0xffffffffu >> (31u - hi_bit)) & (0xffffffffu << lo_bit);
+                    if ((db[w] & mask) != mask) ready = false;
+                }
+            }
+            const unsigned rb = __ballot_sync(kFull, ready);
+            if (rb == 0) {
+                if (++spins > kTSpinMax) { if (lane == 0) { TWATCH(1); sh.abort = 1; } break; }
+                __nanosleep(20);
+                continue;
+            }
+            TC(4, 1);
+            __threadfence_block();                                   // acquire: the bytes behind the bits just read
+            const bool lane_copy = ml <= 32u && !far && period == 0; // short, in the ring, not self-overlapping
+            const uint32_t n = (ready && lane_copy) ? ml : 0u;
+            const uint32_t mx = warp_max_u32(n);
+            for (uint32_t t = 0; t < mx; t += 8) {
+                if (t < n) {
+                    uint32_t lo, hi;
+                    lds_unaligned8(reinterpret_cast<const uint32_t*>(sh.ring), (s + t) & kTRingMask, kTRingMask >> 2, lo, hi);
+                    sts_bytes8(sh.ring, dm + t, lo, hi, n - t);
+                }
+            }
+            unsigned big = __ballot_sync(kFull, ready && !lane_copy);
+            while (big) {
+                const int l = __ffs(big) - 1;
+                big &= big - 1;
+                const uint32_t bs = __shfl_sync(kFull, s, l), bd = __shfl_sync(kFull, dm, l);
+                const uint32_t blen = __shfl_sync(kFull, ml, l), bper = __shfl_sync(kFull, period, l);
+                for (uint32_t j = lane; j < blen; j += 32) {
+                    const uint32_t sp = bs + (bper ? j % bper : j);
+                    const uint8_t v = sp < ring_lo ? st.gout[sp] : sh.ring[sp & kTRingMask];
+                    sh.ring[(bd + j) & kTRingMask] = v;
+                }
+            }
+            __threadfence_block();                                   // release
+            __syncwarp();
+            if (lane == 0) atomicOr(&sh.done_bits[bt], rb);
+            if (ready) pending = false;
+            left &= ~rb;
+        }
+    }
+    __syncthreads();
+    TP(6);
+    if (sh.abort) return -1;
+
+    // ---- ring -> HBM
+    tile_flush(sh, st, g_hi, false);
+    st.op = g_hi;
+    TP(7);
+    if (nexec == nseq) { st.ip = end_ip; return end_special ? 1 : 0; }
+    st.ip = cbase + sh.seq_start[nexec];
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One unit.  Returns bytes produced or kErrCorrupt.  `last` selects the vanilla LZ4 end-of-block rules.
+// ------------------------------------------------------------------------------------------------
+template <class Fmt, bool SNAPPY>
+__device__ __forceinline__ int64_t tile_decode_unit(TileShared<Fmt>& sh, uint32_t& par, const uint8_t* in,
+                                                    uint32_t clen, uint8_t* out, uint32_t cap, bool last) {
+    if (!SNAPPY) {
+        if (clen == 0) return kErrCorrupt;
+        if (cap == 0) return (clen == 1 && in[0] == 0) ? 0 : kErrCorrupt;      // lz4.c:3854-3858
+    }
+    TileState st;
+    const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15);
+    st.gin = in - pad;
+    st.iend = clen + pad;
+    st.a = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15);
+    st.gout = out - st.a;
+    st.cap = st.a + min(cap, kTCapMax);
+    st.ip = pad; st.op = st.a; st.flushed = st.a;
+    st.par = par; st.pend = 0; st.bufc[0] = st.bufc[1] = -1; st.tabc = -1;
+    st.last = last;
+    const uint32_t fast_i_ex = st.iend > kTFastTail + pad ? st.iend - kTFastTail : 0u;
+    int status = 0;
+    while (status == 0) {
+        int slow = 1;
+        if (st.ip < fast_i_ex) slow = tile_group<Fmt>(sh, st, fast_i_ex);
+        TP_DECL
+        if (slow < 0) { status = -1; break; }
+        if (slow) { status = SNAPPY ? tile_slow_step_snappy<Fmt>(sh, st) : tile_slow_step_lz4<Fmt>(sh, st); TC(5, 1); }
+        TP(8);
+    }
+    __syncthreads();
+    if (status > 0) tile_flush(sh, st, st.op, true);
+    tile_wait_buf(sh, st, 0);                                        // nothing may stay in flight into the next unit
+    tile_wait_buf(sh, st, 1);
+    par = st.par;
+    __syncthreads();
+    return status > 0 ? (int64_t)(st.op - st.a) : kErrCorrupt;
+}
+
+template <class Fmt>
+__device__ __forceinline__ void tile_init(TileShared<Fmt>& sh) {
+    if (threadIdx.x == 0) {
+        sh.abort = 0;
+        mbar_init(&sh.bar[0], 1);
+        mbar_init(&sh.bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+}
+
+}  // namespace llc

@@ -134,7 +134,11 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     if (per_sm < 1) per_sm = 1;
     c->ws_blocks = per_sm * c->sm_count;
     if (const char* e = getenv("AOCL_GPU_DECODER"))
-        c->decoder_mode = strcmp(e, "ws") == 0 ? 2 : strcmp(e, "bundle") == 0 ? 3 : 1;
+        c->decoder_mode = strcmp(e, "ws") == 0 ? 2 : strcmp(e, "bundle") == 0 ? 3 : strcmp(e, "tile") == 0 ? 4 : 1;
+    cudaFuncSetAttribute(decode_parts_tile_kernel<TileLz4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileLz4>));
+    cudaFuncSetAttribute(decode_parts_tile_kernel<TileSnappy, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileSnappy>));
+    cudaFuncSetAttribute(decode_pages_tile_kernel<TileLz4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileLz4>));
+    cudaFuncSetAttribute(decode_pages_tile_kernel<TileSnappy, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileSnappy>));
     *out = c;
     return 0;
 }
@@ -165,6 +169,13 @@ extern "C" float aocl_gpu_profile_get(aocl_gpu_ctx_t c, int32_t i, char* name, i
     if (cudaEventElapsedTime(&ms, c->prof_ev[i][0], c->prof_ev[i][1]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
     if (name && name_cap > 0) { strncpy(name, c->prof_name[i], name_cap - 1); name[name_cap - 1] = 0; }
     return ms;
+}
+
+// Diagnostics of the tile decoder: 32 counters (phase cycles with -DLLC_TILE_PROF, watchdog hits always).
+extern "C" int32_t aocl_gpu_debug_counters(uint64_t* out32, int32_t reset) {
+    if (out32 && cudaMemcpyFromSymbol(out32, g_tile_prof, sizeof(uint64_t) * 32) != cudaSuccess) return -2;
+    if (reset) { static const uint64_t zeros[32] = {}; if (cudaMemcpyToSymbol(g_tile_prof, zeros, sizeof(zeros)) != cudaSuccess) return -2; }
+    return 0;
 }
 
 extern "C" int32_t aocl_gpu_partition_count(int32_t codec, size_t n) {
@@ -216,7 +227,14 @@ extern "C" int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t c, int32_t cod
     LLC_LAUNCH(rap_parse_kernel, 1, 1024, 0, c->stream, codec, (const uint8_t*)d_in, (uint64_t)n,
                ranged ? ~0ull : (uint64_t)out_cap, parts, c->d_res);
     const bool warp_decoder = c->decoder_mode == 1;
-    if (c->decoder_mode == 3) {
+    if (c->decoder_mode == 4) {
+        if (codec == AOCL_GPU_LZ4)
+            LLC_LAUNCH((decode_parts_tile_kernel<TileLz4, false>), 2 * c->sm_count, kTThreads, sizeof(TileShared<TileLz4>), c->stream,
+                       (const uint8_t*)d_in, (uint8_t*)d_out, parts, c->d_res, first, count, out_origin);
+        else
+            LLC_LAUNCH((decode_parts_tile_kernel<TileSnappy, true>), 2 * c->sm_count, kTThreads, sizeof(TileShared<TileSnappy>), c->stream,
+                       (const uint8_t*)d_in, (uint8_t*)d_out, parts, c->d_res, first, count, out_origin);
+    } else if (c->decoder_mode == 3) {
         // the partition count is only known on the device here; size bundles for a 1 GiB-class frame
         const uint32_t bundle = 28;
         LLC_LAUNCH(decode_parts_bundle_kernel, c->sm_count, kBThreads, 0, c->stream, codec, (const uint8_t*)d_in,
@@ -375,7 +393,17 @@ extern "C" int32_t aocl_gpu_decompress_batch_async(aocl_gpu_ctx_t c, int32_t cod
     }
     if (count) {
         const bool warp_decoder = c->decoder_mode != 2;
-        if (warp_decoder) {
+        if (c->decoder_mode == 4) {
+            const int grid = (int)(count < (uint64_t)c->sm_count * 2 ? count : (uint64_t)c->sm_count * 2);
+            if (codec == AOCL_GPU_LZ4)
+                LLC_LAUNCH((decode_pages_tile_kernel<TileLz4, false>), grid, kTThreads, sizeof(TileShared<TileLz4>), c->stream,
+                           (const uint8_t* const*)d_in_ptrs, d_in_sizes, (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status,
+                           (uint64_t)count, c->d_res);
+            else
+                LLC_LAUNCH((decode_pages_tile_kernel<TileSnappy, true>), grid, kTThreads, sizeof(TileShared<TileSnappy>), c->stream,
+                           (const uint8_t* const*)d_in_ptrs, d_in_sizes, (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status,
+                           (uint64_t)count, c->d_res);
+        } else if (warp_decoder) {
             const uint64_t blocks = (count + 3) / 4;
             const int grid = (int)(blocks < (uint64_t)c->decode_blocks * 4 ? blocks : (uint64_t)c->decode_blocks * 4);
             LLC_LAUNCH(decode_pages_kernel, grid, 128, 0, c->stream, codec, (const uint8_t* const*)d_in_ptrs, d_in_sizes,

@@ -7,6 +7,7 @@
 #include "lz4_decode_ring.cuh"
 #include "decode_wspec.cuh"
 #include "decode_bundle.cuh"
+#include "decode_tile.cuh"
 
 namespace llc {
 
@@ -262,6 +263,64 @@ __global__ void __launch_bounds__(kBThreads, 1) decode_parts_bundle_kernel(int c
                 if (got < 0 || ((sl.flags & kBExact) && (uint64_t)got != sl.cap)) atomicCAS(&res->error, 0, (int)(base_i + threadIdx.x) + 1);
                 else if (!(sl.flags & kBExact)) res->value = got;       // frame-less LZ4: size is whatever was produced
             }
+        }
+        __syncthreads();
+    }
+}
+
+// Tile variant (decode_tile.cuh): one 512-thread CTA per partition, lane per sequence, 64 KiB output
+// window in shared memory; partitions handed out through the atomic ticket.
+template <class Fmt, bool SNAPPY>
+__global__ void __launch_bounds__(kTThreads, 2) decode_parts_tile_kernel(const uint8_t* __restrict__ in, uint8_t* out,
+                                                                        const PartDesc* __restrict__ parts, CallResult* res,
+                                                                        uint32_t first, uint32_t count, uint64_t origin) {
+    extern __shared__ __align__(128) uint8_t tile_smem[];
+    TileShared<Fmt>& sh = *reinterpret_cast<TileShared<Fmt>*>(tile_smem);
+    if (res->error) return;
+    tile_init(sh);
+    uint32_t par = 0;
+    const uint32_t T = (uint32_t)res->parts;
+    const uint32_t end = min(T, first + min(count, T));
+    for (;;) {
+        if (threadIdx.x == 0) sh.unit = first + atomicAdd(&res->next, 1u);
+        __syncthreads();
+        const uint32_t i = sh.unit;
+        __syncthreads();
+        if (i >= end) break;
+        const PartDesc d = parts[i];
+        if (d.in_len == 0) continue;
+        const int64_t got = tile_decode_unit<Fmt, SNAPPY>(sh, par, in + d.in_off, d.in_len, out + (d.out_off - origin), d.out_len,
+                                                          (d.flags & kPartLast) != 0);
+        if (threadIdx.x == 0) {
+            if (got < 0 || ((d.flags & kPartExact) && (uint64_t)got != d.out_len)) atomicCAS(&res->error, 0, (int)i + 1);
+            else if (!(d.flags & kPartExact)) res->value = got;     // frame-less LZ4: size is whatever was produced
+        }
+    }
+}
+
+template <class Fmt, bool SNAPPY>
+__global__ void __launch_bounds__(kTThreads, 2) decode_pages_tile_kernel(const uint8_t* const* __restrict__ in_ptrs,
+                                                                        const uint32_t* __restrict__ in_sizes, uint8_t* const* out_ptrs,
+                                                                        const uint32_t* __restrict__ out_caps, long long* status,
+                                                                        uint64_t count, CallResult* res) {
+    extern __shared__ __align__(128) uint8_t tile_smem[];
+    TileShared<Fmt>& sh = *reinterpret_cast<TileShared<Fmt>*>(tile_smem);
+    tile_init(sh);
+    uint32_t par = 0;
+    for (uint64_t i = blockIdx.x; i < count; i += gridDim.x) {
+        const uint8_t* in = in_ptrs[i];
+        const uint32_t n = in_sizes[i], cap = out_caps[i];
+        int64_t got;
+        if (!SNAPPY) got = tile_decode_unit<Fmt, false>(sh, par, in, n, out_ptrs[i], cap, true);
+        else {
+            uint32_t total = 0;
+            const uint32_t vb = get_varint32(in, n, &total);
+            if (vb == 0 || total > cap) got = kErrCorrupt;
+            else got = tile_decode_unit<Fmt, true>(sh, par, in + vb, n - vb, out_ptrs[i], total, true);
+        }
+        if (threadIdx.x == 0) {
+            status[i] = got;
+            if (got < 0) atomicAdd(&res->error, 1);
         }
         __syncthreads();
     }

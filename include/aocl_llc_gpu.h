@@ -92,6 +92,10 @@ void aocl_gpu_set_profiling(aocl_gpu_ctx_t ctx, int32_t on);
 int32_t aocl_gpu_profile_count(aocl_gpu_ctx_t ctx);
 float aocl_gpu_profile_get(aocl_gpu_ctx_t ctx, int32_t index, char *name, int32_t name_cap);  /* ms, <0 if n/a */
 
+/* Diagnostics of the tile decoder: copies 32 device counters (per-phase cycles when the library
+ * is built with -DLLC_TILE_PROF, watchdog hits always) and optionally resets them. */
+int32_t aocl_gpu_debug_counters(uint64_t *out32, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif
