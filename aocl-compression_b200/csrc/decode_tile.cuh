@@ -335,7 +335,14 @@ __device__ __forceinline__ void tile_wait_buf(TileShared<Fmt>& sh, TileState& st
 // Caller guarantees (with a __syncthreads) that nobody still reads buffer b.
 template <class Fmt>
 __device__ __forceinline__ void tile_issue_buf(TileShared<Fmt>& sh, TileState& st, int b, int32_t chunk) {
-    tile_wait_buf(sh, st, b);                                        // at most one load per buffer in flight
+    if (st.pend & (1u << b)) {
+        // At most one load per buffer in flight.  EVERY thread has to observe the old phase before thread 0
+        // re-arms the barrier: a warp that polls late would otherwise find the barrier two phases on, read
+        // its parity as "not completed yet" and spin until the watchdog (seen as an intermittent failure on
+        // streams whose long literal runs make every group jump over an unconsumed prefetch).
+        tile_wait_buf(sh, st, b);
+        __syncthreads();
+    }
     const uint32_t base = (uint32_t)chunk << kTChunkLog;
     st.bufc[b] = chunk;
     if (base >= st.iend) return;

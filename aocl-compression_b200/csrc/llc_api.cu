@@ -3,8 +3,15 @@
 // 253-304 of the reference: same argument checks, same return values, same statistics.
 //
 // Buffers may live on the host (pageable or pinned) or on the device; host buffers are staged
-// through HBM with cudaMemcpyAsync on the context's stream, so measureStats timings include
-// the PCIe transfers exactly like the reference's timings include its memcpy epilogues.
+// through HBM, so measureStats timings include the PCIe transfers exactly like the reference's
+// timings include its memcpy epilogues.  Large pinned host buffers are pipelined:
+//   compress   the input goes up in pieces on a copy stream while the encoder is already running
+//              behind an input watermark (LZ4: stripes across all partitions, because every partition
+//              is one serial chain that has to start early; Snappy: in order, fragments are taken in
+//              order);
+//   decompress the stream is cut into slabs of partitions: H2D of slab k+1 | decode of slab k | D2H
+//              of slab k-1 on three streams.
+// Pageable buffers and small calls take the plain copy - run - copy sequence.
 #include "../../include/aocl_llc.h"
 #include "../../include/aocl_llc_gpu.h"
 
@@ -32,8 +39,38 @@ struct Global {
     bool lz4_setup_done = false;   // setup is once-only until destroy (lz4.c:4999-5016)
     bool lz4_frameless = false;
     bool snappy_setup_done = false;
+    // pipelined host transfers
+    cudaStream_t up = nullptr, down = nullptr;         // H2D / D2H copy streams
+    uint32_t* d_flag = nullptr;                        // input watermark (device)
+    uint32_t* h_marks = nullptr;                       // pinned source values for the watermark copies
+    cudaEvent_t ev[2 * 64 + 2] = {};
+    bool pipe_ready = false, pipe_failed = false;
 };
 Global g;
+
+constexpr int kMaxPieces = 64;
+constexpr size_t kPipeMinBytes = size_t(8) << 20;      // below this the plain sequence is as fast
+
+bool ensure_pipe() {
+    if (g.pipe_ready) return true;
+    if (g.pipe_failed || getenv("AOCL_GPU_NO_PIPELINE")) return false;
+    bool ok = cudaStreamCreateWithFlags(&g.up, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&g.down, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&g.d_flag, 256) == cudaSuccess &&
+              cudaMallocHost(&g.h_marks, sizeof(uint32_t) * (kMaxPieces + 1)) == cudaSuccess;
+    for (auto& e : g.ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); g.pipe_failed = true; return false; }
+    g.pipe_ready = true;
+    return true;
+}
+
+bool pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+uint32_t rd32(const unsigned char* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
 bool ensure_ctx() {
     if (g.ctx) return true;
@@ -70,6 +107,119 @@ uint64_t now_ns() {
     return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
 }
 
+// Enqueue the H2D transfer of a pinned host input on the copy stream in pieces, each followed by a
+// 4-byte copy that raises the encoder's input watermark (include/aocl_llc_gpu.h), and make the
+// compute stream wait only for the watermark reset.  Returns false if this input takes the plain path.
+bool stream_input_up(int codec, const char* in, size_t n, void* d_in, cudaStream_t s) {
+    if (n < kPipeMinBytes || !pinned_host(in) || !ensure_pipe()) return false;
+    const uint32_t T = (uint32_t)aocl_gpu_partition_count(codec, n);
+    if (T < 2 || (codec == LZ4 && g.lz4_frameless)) return false;
+    bool ok = cudaMemsetAsync(g.d_flag, 0, sizeof(uint32_t), g.up) == cudaSuccess &&
+              cudaEventRecord(g.ev[0], g.up) == cudaSuccess && cudaStreamWaitEvent(s, g.ev[0], 0) == cudaSuccess;
+    int pieces = 0;
+    if (codec == LZ4) {
+        // stripe j = bytes [j*w, (j+1)*w) of EVERY partition (a 2-D copy, pitch = partition size)
+        const size_t common = n / T, w = 16384;
+        pieces = (int)(common / w);
+        if (pieces < 1) pieces = 1;
+        if (pieces > kMaxPieces) pieces = kMaxPieces;
+        for (int j = 0; j < pieces && ok; j++) {
+            const size_t lo = (size_t)j * w, width = (j == pieces - 1) ? common - lo : w;
+            ok = cudaMemcpy2DAsync((char*)d_in + lo, common, in + lo, common, width, T, cudaMemcpyHostToDevice, g.up) == cudaSuccess;
+            if (ok && j == pieces - 1 && n > common * T)     // the last partition's n % T extra bytes
+                ok = cudaMemcpyAsync((char*)d_in + common * T, in + common * T, n - common * T, cudaMemcpyHostToDevice, g.up) == cudaSuccess;
+            g.h_marks[j] = (j == pieces - 1) ? 0xffffffffu : (uint32_t)(lo + width);
+            ok = ok && cudaMemcpyAsync(g.d_flag, &g.h_marks[j], sizeof(uint32_t), cudaMemcpyHostToDevice, g.up) == cudaSuccess;
+        }
+    } else {
+        const size_t piece = size_t(32) << 20;
+        pieces = (int)((n + piece - 1) / piece);
+        for (int j = 0; j < pieces && ok; j++) {
+            const size_t lo = (size_t)j * piece, len = (j == pieces - 1) ? n - lo : piece;
+            ok = cudaMemcpyAsync((char*)d_in + lo, in + lo, len, cudaMemcpyHostToDevice, g.up) == cudaSuccess;
+            g.h_marks[j] = (j == pieces - 1) ? 0xffffffffu : (uint32_t)(lo + len);
+            ok = ok && cudaMemcpyAsync(g.d_flag, &g.h_marks[j], sizeof(uint32_t), cudaMemcpyHostToDevice, g.up) == cudaSuccess;
+        }
+    }
+    if (!ok) {                                              // whatever was enqueued must drain before the plain path reuses d_in
+        cudaGetLastError();
+        cudaStreamSynchronize(g.up);
+        return false;
+    }
+    aocl_gpu_set_input_watermark(g.ctx, g.d_flag);
+    return true;
+}
+
+// Host-to-host decompress of a well-formed multi-partition RAP stream in slabs.  Returns bytes
+// produced, -1 on failure, or -100 when the stream does not qualify (caller takes the plain path,
+// which also produces the reference's error behaviour for malformed frames).
+int64_t decompress_pipelined(int codec, const char* in, size_t n, char* out, size_t out_size, cudaStream_t s) {
+    const unsigned char* u = (const unsigned char*)in;
+    uint64_t magic = 0;
+    if (n < kPipeMinBytes || n > 0xffffffffull) return -100;
+    memcpy(&magic, u, 8);
+    if (magic != kRapMagic) return -100;
+    const uint32_t frame = rd32(u + 8), T = rd32(u + 12);
+    if (T < 64 || T > 65536 || frame != 16 + 12 * (uint64_t)T || frame > n) return -100;
+    if (!pinned_host(in) || !pinned_host(out) || !ensure_pipe()) return -100;
+    // A slab is one wave of the tile decoder (one partition per resident CTA, two CTAs per SM), so the
+    // slab decodes cost what the single launch costs; at most 24 slabs.  Entries must be laid out back
+    // to back in order.
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint32_t per = sms > 0 ? 2u * (uint32_t)sms : 256u;
+    while ((T + per - 1) / per > 24) per += sms > 0 ? 2u * (uint32_t)sms : 256u;
+    const int K = (int)((T + per - 1) / per);
+    if (K < 2) return -100;
+    uint64_t in_end[24], out_end[24];
+    uint32_t first[25];
+    uint64_t pos = frame, total = 0;
+    for (int k = 0; k < K; k++) first[k] = (uint32_t)k * per;
+    first[K] = T;
+    for (int k = 0; k < K; k++) {
+        for (uint32_t i = first[k]; i < first[k + 1]; i++) {
+            const unsigned char* e = u + 16 + 12 * (size_t)i;
+            const uint64_t off = rd32(e), clen = rd32(e + 4), dlen = rd32(e + 8);
+            if (off < pos || off + clen > n) return -100;
+            pos = off + clen;
+            if (clen) total += dlen;
+        }
+        in_end[k] = (k == K - 1) ? n : pos;
+        out_end[k] = total;
+    }
+    if (total > out_size || total == 0) return -100;
+    if (!grow(&g.d_in, &g.d_in_bytes, n) || !grow(&g.d_out, &g.d_out_bytes, total)) return -1;
+
+    bool ok = true;
+    uint64_t lo = 0;
+    for (int k = 0; k < K && ok; k++) {                     // all uploads, in order, on the copy stream
+        ok = cudaMemcpyAsync((char*)g.d_in + lo, in + lo, in_end[k] - lo, cudaMemcpyHostToDevice, g.up) == cudaSuccess &&
+             cudaEventRecord(g.ev[1 + k], g.up) == cudaSuccess;
+        lo = in_end[k];
+    }
+    ok = ok && cudaStreamWaitEvent(s, g.ev[1], 0) == cudaSuccess &&
+         aocl_gpu_decompress_open_async(g.ctx, codec, g.d_in, n, out_size) == 0;
+    uint64_t olo = 0;
+    for (int k = 0; k < K && ok; k++) {
+        ok = cudaStreamWaitEvent(s, g.ev[1 + k], 0) == cudaSuccess &&
+             aocl_gpu_decompress_slab_async(g.ctx, codec, g.d_in, g.d_out, first[k], first[k + 1] - first[k]) == 0 &&
+             cudaEventRecord(g.ev[1 + kMaxPieces + k], s) == cudaSuccess &&
+             cudaStreamWaitEvent(g.down, g.ev[1 + kMaxPieces + k], 0) == cudaSuccess;
+        if (ok && out_end[k] > olo)
+            ok = cudaMemcpyAsync(out + olo, (char*)g.d_out + olo, out_end[k] - olo, cudaMemcpyDeviceToHost, g.down) == cudaSuccess;
+        olo = out_end[k];
+    }
+    if (ok) ok = aocl_gpu_decompress_close_async(g.ctx) == 0;
+    const int64_t r = ok ? aocl_gpu_finish(g.ctx) : -1;
+    cudaStreamSynchronize(g.up);
+    cudaStreamSynchronize(s);
+    const bool down_ok = cudaStreamSynchronize(g.down) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    if (r < 0 || !down_ok || (uint64_t)r != total) return -1;
+    return r;
+}
+
 // Returns bytes produced or a negative codec error (the adapters' CODEC_ERROR).
 int64_t run_codec(bool compress, int codec, char* in, size_t in_size, char* out, size_t out_size) {
     std::lock_guard<std::mutex> lock(g.mu);
@@ -85,13 +235,20 @@ int64_t run_codec(bool compress, int codec, char* in, size_t in_size, char* out,
         if (codec == LZ4 && out == nullptr) return -1;
     }
 
+    const bool in_dev = in_size ? on_device(in) : true;
+    const bool out_dev = on_device(out);
+    if (!compress && !in_dev && !out_dev) {
+        const int64_t r = decompress_pipelined(codec, in, in_size, out, out_size, s);
+        if (r != -100) return r;
+    }
     const void* d_in = in;
-    if (in_size && !on_device(in)) {
+    bool streamed = false;
+    if (in_size && !in_dev) {
         if (!grow(&g.d_in, &g.d_in_bytes, in_size)) return -1;
-        if (cudaMemcpyAsync(g.d_in, in, in_size, cudaMemcpyHostToDevice, s) != cudaSuccess) { cudaGetLastError(); return -1; }
+        if (compress) streamed = stream_input_up(codec, in, in_size, g.d_in, s);
+        if (!streamed && cudaMemcpyAsync(g.d_in, in, in_size, cudaMemcpyHostToDevice, s) != cudaSuccess) { cudaGetLastError(); return -1; }
         d_in = g.d_in;
     }
-    const bool out_dev = on_device(out);
     void* d_out = out;
     size_t stage_cap = out_size;
     if (!out_dev) {
@@ -103,6 +260,7 @@ int64_t run_codec(bool compress, int codec, char* in, size_t in_size, char* out,
     if (compress) aocl_gpu_compress_async(g.ctx, codec, d_in, in_size, d_out, out_size);
     else          aocl_gpu_decompress_async(g.ctx, codec, d_in, in_size, d_out, out_size);
     const int64_t r = aocl_gpu_finish(g.ctx);
+    if (streamed) cudaStreamSynchronize(g.up);              // nothing of this call may still be in flight
     if (r < 0) return -1;
     if (!out_dev && r > 0) {
         if ((size_t)r > stage_cap) return -1;

@@ -120,6 +120,36 @@ __device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v, int lane) {
     return v;
 }
 
+// ---- input gate: encoders that start while their input is still arriving over PCIe ---------
+// The host enqueues the H2D copies of a host-resident input in pieces on a copy stream and, after
+// each piece, a 4-byte copy that raises a watermark word in HBM.  An encoder warp calls wait(need)
+// before it touches input bytes below `need`; with a null flag (device-resident input) the gate
+// is free.  The watermark counts bytes available in EVERY partition (LZ4: the input is sent in
+// stripes across all partitions, because each partition is one serial chain that has to start
+// early) or bytes available from the start of the buffer (Snappy: fragments are taken in order).
+// A watermark that never arrives (a copy failed) ends the wait after ~2 s and flags the call.
+struct InGate {
+    const uint32_t* flag;
+    int* error;
+    uint32_t have;
+    __device__ __forceinline__ InGate(const uint32_t* f, int* e) : flag(f), error(e), have(f ? 0u : 0xffffffffu) {}
+    __device__ __forceinline__ void wait(uint32_t need) {
+        if (need <= have) return;                        // `have` starts at 0xffffffff when there is no flag
+        uint32_t spins = 0;
+        for (;;) {
+            have = *reinterpret_cast<const volatile uint32_t*>(flag);
+            if (have >= need) break;
+            if (*reinterpret_cast<volatile int*>(error) != 0 || ++spins > (1u << 23)) {
+                atomicExch(error, 1);
+                have = 0xffffffffu;                      // give up: the call fails, nothing may hang
+                break;
+            }
+            __nanosleep(256);
+        }
+        __syncwarp();
+    }
+};
+
 // ---- partition arithmetic (threads/threads.c:55-97 of the reference) ----------------------
 __host__ __device__ inline uint32_t partition_count(uint64_t n, uint32_t window) {
     const uint64_t chunk = (uint64_t)window * kWindowFactor;

@@ -22,6 +22,7 @@ static std::atomic<uint64_t> g_launches{0};
     } while (0)
 
 constexpr int kProfSlots = 16;
+constexpr int kStabMax = 11;        // shared-table LZ4 encoder CTAs per SM (16 KiB table + 4 KiB owner bytes each)
 
 struct aocl_gpu_ctx_s {
     int device = 0;
@@ -46,11 +47,14 @@ struct aocl_gpu_ctx_s {
     int decode_blocks = 0;          // persistent grid size of decode_parts_kernel
     int ws_blocks = 0;              // persistent grid size of decode_parts_ws_kernel
     // Decoder organisation (AOCL_GPU_DECODER).  Measured on B200, 1 GiB frames (LZ4 text / Snappy log):
-    //   warp   (default) one warp per partition: LZ4 TMA-ring pipelined decoder 14.1 ms, Snappy 11.4 ms
+    //   tile   (default) one 512-thread CTA per partition, lane per sequence:    11.2 ms  / 8.5 ms
+    //   warp   one warp per partition: LZ4 TMA-ring pipelined decoder            14.2 ms  / 11.9 ms
     //   ws     parser warp + lane-per-sequence copier warp per partition:        16-19 ms / 15.5 ms
     //   bundle 32 lane-parsers + 16 copier warps per CTA:                        22 ms    / 18 ms
-    int decoder_mode = 1;
+    int decoder_mode = 4;
+    int pages_mode = 1;             // batched pages: a million independent units keep warp-per-page busy; env overrides
     bool lz4_frameless = false;
+    const uint32_t* in_flag = nullptr;   // one-shot input watermark for the next compress (aocl_gpu_set_input_watermark)
     bool batch_mode = false;        // last enqueue was a batch call (finish() returns -failures)
     int last_rc = 0;                // enqueue-time failure to report from finish()
     // optional per-kernel timing (aocl_gpu_set_profiling)
@@ -118,7 +122,7 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     }
     if (const char* e = getenv("AOCL_GPU_GTAB_CTAS")) c->gtab_ctas_per_sm = atoi(e);
     if (const char* e = getenv("AOCL_GPU_SNAPPY_GTAB_CTAS")) c->snappy_gtab_ctas_per_sm = atoi(e);
-    if (const char* e = getenv("AOCL_GPU_STAB_CTAS")) c->stab_ctas_per_sm = atoi(e) > 14 ? 14 : atoi(e);
+    if (const char* e = getenv("AOCL_GPU_STAB_CTAS")) c->stab_ctas_per_sm = atoi(e) > kStabMax ? kStabMax : atoi(e);
 
     // opt in to the shared-memory sizes the encoders need (16 KiB LZ4 table, 32 KiB Snappy table)
     cudaFuncSetAttribute(lz4_encode_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
@@ -134,7 +138,7 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     if (per_sm < 1) per_sm = 1;
     c->ws_blocks = per_sm * c->sm_count;
     if (const char* e = getenv("AOCL_GPU_DECODER"))
-        c->decoder_mode = strcmp(e, "ws") == 0 ? 2 : strcmp(e, "bundle") == 0 ? 3 : strcmp(e, "tile") == 0 ? 4 : 1;
+        c->pages_mode = c->decoder_mode = strcmp(e, "ws") == 0 ? 2 : strcmp(e, "bundle") == 0 ? 3 : strcmp(e, "warp") == 0 ? 1 : 4;
     cudaFuncSetAttribute(decode_parts_tile_kernel<TileLz4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileLz4>));
     cudaFuncSetAttribute(decode_parts_tile_kernel<TileSnappy, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileSnappy>));
     cudaFuncSetAttribute(decode_pages_tile_kernel<TileLz4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileLz4>));
@@ -160,6 +164,7 @@ extern "C" void aocl_gpu_ctx_destroy(aocl_gpu_ctx_t c) {
 
 extern "C" void* aocl_gpu_ctx_stream(aocl_gpu_ctx_t c) { return c ? (void*)c->stream : nullptr; }
 extern "C" void aocl_gpu_set_lz4_frameless(aocl_gpu_ctx_t c, int32_t on) { if (c) c->lz4_frameless = on != 0; }
+extern "C" void aocl_gpu_set_input_watermark(aocl_gpu_ctx_t c, const uint32_t* d_flag) { if (c) c->in_flag = d_flag; }
 extern "C" uint64_t aocl_gpu_launch_count(void) { return g_launches.load(); }
 extern "C" void aocl_gpu_set_profiling(aocl_gpu_ctx_t c, int32_t on) { if (c) c->prof = on != 0; }
 extern "C" int32_t aocl_gpu_profile_count(aocl_gpu_ctx_t c) { return c ? c->prof_n : 0; }
@@ -205,12 +210,22 @@ extern "C" int64_t aocl_gpu_finish(aocl_gpu_ctx_t c) {
     if (!cuda_ok(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize")) return -2;
     if (!cuda_ok(cudaGetLastError(), "kernel")) return -2;
     if (c->batch_mode) return -(int64_t)c->h_res->error;
+    if (c->h_res->error && getenv("AOCL_GPU_VERBOSE")) {
+        uint64_t cnt[32] = {};
+        cudaMemcpyFromSymbol(cnt, g_tile_prof, sizeof(cnt));
+        fprintf(stderr, "[aocl-llc-b200] call failed: error=%d value=%lld parts=%d next=%u watchdog=[%llu %llu %llu %llu]\n",
+                c->h_res->error, c->h_res->value, c->h_res->parts, c->h_res->next, (unsigned long long)cnt[24],
+                (unsigned long long)cnt[25], (unsigned long long)cnt[26], (unsigned long long)cnt[27]);
+    }
     if (c->h_res->error) return -2;
     return c->h_res->value;
 }
 
 // ---------------------------------------------------------------------------------- decompress
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void launch_decode_range(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, void* d_out, PartDesc* parts,
+                                uint32_t first, uint32_t count, uint64_t out_origin);
 
 extern "C" int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, size_t n,
                                                    void* d_out, size_t out_cap, uint32_t first, uint32_t count,
@@ -226,7 +241,17 @@ extern "C" int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t c, int32_t cod
     // for a range the capacity check applies to the range, not to the whole stream
     LLC_LAUNCH(rap_parse_kernel, 1, 1024, 0, c->stream, codec, (const uint8_t*)d_in, (uint64_t)n,
                ranged ? ~0ull : (uint64_t)out_cap, parts, c->d_res);
-    const bool warp_decoder = c->decoder_mode == 1;
+    launch_decode_range(c, codec, d_in, d_out, parts, first, count, out_origin);
+    if (ranged) LLC_LAUNCH(range_total_kernel, 1, 256, 0, c->stream, parts, c->d_res, first, count);
+    end_call(c);
+    return 0;
+}
+
+// Slab-wise decode of one stream: open (frame parse) / slab (a partition range, fresh ticket, sticky
+// error) / close.  The caller orders the slabs against its own H2D / D2H copies with events on the
+// context's stream; aocl_gpu_finish() then returns the stream's total or the first error.
+static void launch_decode_range(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, void* d_out, PartDesc* parts,
+                                uint32_t first, uint32_t count, uint64_t out_origin) {
     if (c->decoder_mode == 4) {
         if (codec == AOCL_GPU_LZ4)
             LLC_LAUNCH((decode_parts_tile_kernel<TileLz4, false>), 2 * c->sm_count, kTThreads, sizeof(TileShared<TileLz4>), c->stream,
@@ -239,13 +264,34 @@ extern "C" int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t c, int32_t cod
         const uint32_t bundle = 28;
         LLC_LAUNCH(decode_parts_bundle_kernel, c->sm_count, kBThreads, 0, c->stream, codec, (const uint8_t*)d_in,
                    (uint8_t*)d_out, parts, c->d_res, first, count, out_origin, bundle);
-    } else if (warp_decoder)
+    } else if (c->decoder_mode == 1)
         LLC_LAUNCH(decode_parts_kernel, c->decode_blocks, 128, 0, c->stream, codec, (const uint8_t*)d_in, (uint8_t*)d_out,
                    parts, c->d_res, first, count, out_origin);
     else
         LLC_LAUNCH(decode_parts_ws_kernel, c->ws_blocks, 64, 0, c->stream, codec, (const uint8_t*)d_in, (uint8_t*)d_out,
                    parts, c->d_res, first, count, out_origin);
-    if (ranged) LLC_LAUNCH(range_total_kernel, 1, 256, 0, c->stream, parts, c->d_res, first, count);
+}
+
+extern "C" int32_t aocl_gpu_decompress_open_async(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, size_t n, size_t out_cap) {
+    if (!c) return -5;
+    begin_call(c);
+    if ((codec != AOCL_GPU_LZ4 && codec != AOCL_GPU_SNAPPY) || !d_in || n == 0 || n > 0xffffffffull) { c->last_rc = -2; return -2; }
+    if (!ensure_ws(c, sizeof(PartDesc) * kMaxPartitions)) { c->last_rc = -2; return -2; }
+    LLC_LAUNCH(rap_parse_kernel, 1, 1024, 0, c->stream, codec, (const uint8_t*)d_in, (uint64_t)n, (uint64_t)out_cap,
+               reinterpret_cast<PartDesc*>(c->ws), c->d_res);
+    return 0;
+}
+extern "C" int32_t aocl_gpu_decompress_slab_async(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, void* d_out,
+                                                  uint32_t first, uint32_t count) {
+    if (!c) return -5;
+    if (c->last_rc) return c->last_rc;
+    cudaMemsetAsync(&c->d_res->next, 0, sizeof(unsigned int), c->stream);
+    launch_decode_range(c, codec, d_in, d_out, reinterpret_cast<PartDesc*>(c->ws), first, count, 0);
+    return 0;
+}
+extern "C" int32_t aocl_gpu_decompress_close_async(aocl_gpu_ctx_t c) {
+    if (!c) return -5;
+    if (c->last_rc) return c->last_rc;
     end_call(c);
     return 0;
 }
@@ -265,6 +311,8 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
                                            size_t out_cap) {
     if (!c) return -5;
     begin_call(c);
+    const uint32_t* in_flag = c->in_flag;                      // one-shot
+    c->in_flag = nullptr;
     if ((codec != AOCL_GPU_LZ4 && codec != AOCL_GPU_SNAPPY) || (!d_in && n) || !d_out || out_cap == 0 || n > 0x7E000000ull) {
         c->last_rc = -2; return -2;
     }
@@ -281,11 +329,11 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
             const uint64_t slot = align_up(pmax + pmax / 255 + 32, 256);
             int stab = c->stab_ctas_per_sm, gtab = c->gtab_ctas_per_sm;
             if (stab < 0 && gtab < 0) {                        // auto: one wave if at all possible
-                if (T <= (uint32_t)c->sm_count * 14u) { stab = 14; gtab = 0; } else { stab = 0; gtab = 32; }
+                if (T <= (uint32_t)c->sm_count * (uint32_t)kStabMax) { stab = kStabMax; gtab = 0; } else { stab = 0; gtab = 32; }
             }
-            if (stab < 0) stab = gtab > 0 ? 0 : 14;
+            if (stab < 0) stab = gtab > 0 ? 0 : kStabMax;
             if (gtab < 0) gtab = 0;
-            if (stab == 0 && gtab == 0) stab = 14;
+            if (stab == 0 && gtab == 0) stab = kStabMax;
             const int g_ctas = gtab * c->sm_count;
             const size_t o_rec = 0, o_plan = align_up(o_rec + sizeof(Lz4Rec) * T + 256, 256);
             const size_t o_tab = align_up(o_plan + sizeof(Lz4Plan) * T, 256);
@@ -316,12 +364,12 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
                     cudaStreamSetAttribute(c->side, cudaStreamAttributeAccessPolicyWindow, &av);
                 }
                 lz4_encode_parts_gtab_kernel<<<(int)(T < (uint32_t)g_ctas ? T : (uint32_t)g_ctas), 32, 0, c->side>>>(
-                    src, (uint64_t)n, T, scratch, slot, rec, ticket, tables);
+                    src, (uint64_t)n, T, scratch, slot, rec, ticket, tables, in_flag, c->d_res);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
                 cudaEventRecord(c->ev_join, c->side);
             }
             if (a_grid > 0) {
-                lz4_encode_parts_kernel<<<a_grid, 32, 16384, c->stream>>>(src, (uint64_t)n, T, scratch, slot, rec, ticket);
+                lz4_encode_parts_kernel<<<a_grid, 32, 16384, c->stream>>>(src, (uint64_t)n, T, scratch, slot, rec, ticket, in_flag, c->d_res);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
             }
             if (g_ctas > 0 && T > (uint32_t)a_grid) cudaStreamWaitEvent(c->stream, c->ev_join, 0);
@@ -362,9 +410,9 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
         }
-        if (F && g_grid) LLC_LAUNCH(snappy_encode_frags_gtab_kernel, g_grid, 32, 0, c->stream, src, g, scratch, slot, frag_len, ticket, tables);
+        if (F && g_grid) LLC_LAUNCH(snappy_encode_frags_gtab_kernel, g_grid, 32, 0, c->stream, src, g, scratch, slot, frag_len, ticket, tables, in_flag, c->d_res);
         else if (F) LLC_LAUNCH(snappy_encode_frags_kernel, (F < (uint32_t)c->sm_count * 7u ? F : (uint32_t)c->sm_count * 7u), 32, 32768,
-                               c->stream, src, g, scratch, slot, frag_len, ticket);
+                               c->stream, src, g, scratch, slot, frag_len, ticket, in_flag, c->d_res);
         if (F && g_grid && c->l2_persist_bytes) {              // later kernels on this stream: no window
             cudaStreamAttrValue av = {};
             cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
@@ -392,8 +440,8 @@ extern "C" int32_t aocl_gpu_decompress_batch_async(aocl_gpu_ctx_t c, int32_t cod
         c->last_rc = -2; return -2;
     }
     if (count) {
-        const bool warp_decoder = c->decoder_mode != 2;
-        if (c->decoder_mode == 4) {
+        const bool warp_decoder = c->pages_mode != 2;
+        if (c->pages_mode == 4) {
             const int grid = (int)(count < (uint64_t)c->sm_count * 2 ? count : (uint64_t)c->sm_count * 2);
             if (codec == AOCL_GPU_LZ4)
                 LLC_LAUNCH((decode_pages_tile_kernel<TileLz4, false>), grid, kTThreads, sizeof(TileShared<TileLz4>), c->stream,
@@ -429,7 +477,7 @@ extern "C" int32_t aocl_gpu_compress_batch_async(aocl_gpu_ctx_t c, int32_t codec
     }
     if (count) {
         const size_t smem = codec == AOCL_GPU_LZ4 ? 16384 : 32768;
-        const uint64_t max_grid = (uint64_t)c->sm_count * (codec == AOCL_GPU_LZ4 ? 14 : 7) * 4;
+        const uint64_t max_grid = (uint64_t)c->sm_count * (codec == AOCL_GPU_LZ4 ? kStabMax : 6) * 4;
         const int grid = (int)(count < max_grid ? count : max_grid);
         LLC_LAUNCH(encode_pages_kernel, grid, 32, smem, c->stream, codec, (const uint8_t* const*)d_in_ptrs, d_in_sizes,
                    (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status, (uint64_t)count, c->d_res);

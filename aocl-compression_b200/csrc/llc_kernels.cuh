@@ -3,6 +3,7 @@
 #pragma once
 #include "llc_common.cuh"
 #include "lz4_codec.cuh"
+#include "lz4_encode_lean.cuh"
 #include "snappy_codec.cuh"
 #include "lz4_decode_ring.cuh"
 #include "decode_wspec.cuh"
@@ -379,6 +380,7 @@ __global__ void __launch_bounds__(32) encode_pages_kernel(int codec, const uint8
                                                           const uint32_t* __restrict__ out_caps, long long* status,
                                                           uint64_t count, CallResult* res) {
     extern __shared__ __align__(16) uint32_t tab_mem[];
+    __shared__ uint8_t own_mem[kLeanOwnBytes];
     const int lane = lane_id();
     for (uint64_t i = blockIdx.x; i < count; i += gridDim.x) {
         const uint8_t* in = in_ptrs[i];
@@ -387,7 +389,8 @@ __global__ void __launch_bounds__(32) encode_pages_kernel(int codec, const uint8
         int64_t got;
         if (codec == 0) {
             const uint64_t bound = (uint64_t)n + n / 255 + 16;
-            got = (cap == 0) ? 0 : lz4_encode_warp(in, n, dst, cap >= bound ? -1 : (int64_t)cap, true, nullptr, tab_mem, lane);
+            InGate gate(nullptr, nullptr);
+            got = (cap == 0) ? 0 : lz4_encode_unit(in, n, dst, cap >= bound ? -1 : (int64_t)cap, true, nullptr, tab_mem, own_mem, lane, gate);
             if (got == 0) got = kErrCorrupt;
         } else if ((uint64_t)cap < 32ull + n + n / 6) {
             got = kErrCorrupt;                                  // api/codec.cpp:262-265
@@ -423,8 +426,9 @@ struct Lz4Rec { uint32_t body_len; uint32_t tail_len; };
 // so its warps fill the remaining warp slots of each SM.  Both produce identical bytes.
 __device__ __forceinline__ void lz4_encode_parts_loop(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
                                                       uint8_t* scratch, uint64_t slot, Lz4Rec* rec, uint32_t* ticket,
-                                                      uint32_t* tab_mem) {
+                                                      uint32_t* tab_mem, uint8_t* own, const uint32_t* in_flag, CallResult* res) {
     const int lane = lane_id();
+    InGate gate(in_flag, &res->error);                       // watermark: bytes present in every partition
     const uint64_t common = n / T, left = n % T;             // threads/threads.c:91-97,127-135
     for (;;) {
         uint32_t i = 0;
@@ -433,20 +437,24 @@ __device__ __forceinline__ void lz4_encode_parts_loop(const uint8_t* __restrict_
         if (i >= T) break;
         const uint32_t pn = (uint32_t)(common + (i == T - 1 ? left : 0));
         uint32_t tail = 0;
-        const uint32_t body = lz4_encode_warp(src + common * i, pn, scratch + slot * i, -1, i == T - 1, &tail, tab_mem, lane);
+        const uint32_t body = lz4_encode_unit(src + common * i, pn, scratch + slot * i, -1, i == T - 1, &tail, tab_mem, own, lane, gate);
         if (lane == 0) { rec[i].body_len = body; rec[i].tail_len = tail; }
         __syncwarp();
     }
 }
 __global__ void __launch_bounds__(32) lz4_encode_parts_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
-                                                              uint8_t* scratch, uint64_t slot, Lz4Rec* rec, uint32_t* ticket) {
+                                                              uint8_t* scratch, uint64_t slot, Lz4Rec* rec, uint32_t* ticket,
+                                                              const uint32_t* in_flag, CallResult* res) {
     extern __shared__ __align__(16) uint32_t tab_mem[];
-    lz4_encode_parts_loop(src, n, T, scratch, slot, rec, ticket, tab_mem);
+    __shared__ uint8_t own_mem[kLeanOwnBytes];
+    lz4_encode_parts_loop(src, n, T, scratch, slot, rec, ticket, tab_mem, own_mem, in_flag, res);
 }
 __global__ void __launch_bounds__(32) lz4_encode_parts_gtab_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
                                                                    uint8_t* scratch, uint64_t slot, Lz4Rec* rec,
-                                                                   uint32_t* ticket, uint32_t* tables) {
-    lz4_encode_parts_loop(src, n, T, scratch, slot, rec, ticket, tables + (size_t)blockIdx.x * 4096);
+                                                                   uint32_t* ticket, uint32_t* tables,
+                                                                   const uint32_t* in_flag, CallResult* res) {
+    __shared__ uint8_t own_mem[kLeanOwnBytes];
+    lz4_encode_parts_loop(src, n, T, scratch, slot, rec, ticket, tables + (size_t)blockIdx.x * 4096, own_mem, in_flag, res);
 }
 
 // Frame-less block written straight to the destination (T == 1, lz4.c:2674-2677).
@@ -454,7 +462,9 @@ __global__ void __launch_bounds__(32) lz4_encode_single_kernel(const uint8_t* __
                                                                long long cap, CallResult* res) {
     extern __shared__ __align__(16) uint32_t tab_mem[];
     const int lane = lane_id();
-    const uint32_t got = lz4_encode_warp(src, n, dst, cap, true, nullptr, tab_mem, lane);
+    __shared__ uint8_t own_mem[kLeanOwnBytes];
+    InGate gate(nullptr, nullptr);
+    const uint32_t got = lz4_encode_unit(src, n, dst, cap, true, nullptr, tab_mem, own_mem, lane, gate);
     if (lane == 0) {
         if (got == 0) { res->error = 1; res->value = kErrCorrupt; }
         else res->value = got;
@@ -630,8 +640,10 @@ __device__ __forceinline__ void snappy_locate(const SnappyGeom& g, uint32_t f, u
 }
 
 __device__ __forceinline__ void snappy_encode_frags_loop(const uint8_t* __restrict__ src, const SnappyGeom& g, uint8_t* scratch,
-                                                         uint64_t slot, uint32_t* frag_len, uint32_t* ticket, uint16_t* tab) {
+                                                         uint64_t slot, uint32_t* frag_len, uint32_t* ticket, uint16_t* tab,
+                                                         const uint32_t* in_flag, CallResult* res) {
     const int lane = lane_id();
+    InGate gate(in_flag, &res->error);                       // watermark: bytes present from the start of the input
     for (;;) {
         uint32_t f = 0;
         if (lane == 0) f = atomicAdd(ticket, 1u);
@@ -639,6 +651,7 @@ __device__ __forceinline__ void snappy_encode_frags_loop(const uint8_t* __restri
         if (f >= g.frags_total) break;
         uint32_t part, len; uint64_t off;
         snappy_locate(g, f, &part, &off, &len);
+        gate.wait((uint32_t)(off + len));
         const uint32_t got = snappy_encode_fragment_warp(src + off, len, scratch + slot * f, tab, lane);
         if (lane == 0) frag_len[f] = got;
         __syncwarp();
@@ -646,14 +659,15 @@ __device__ __forceinline__ void snappy_encode_frags_loop(const uint8_t* __restri
 }
 __global__ void __launch_bounds__(32) snappy_encode_frags_kernel(const uint8_t* __restrict__ src, SnappyGeom g,
                                                                  uint8_t* scratch, uint64_t slot, uint32_t* frag_len,
-                                                                 uint32_t* ticket) {
+                                                                 uint32_t* ticket, const uint32_t* in_flag, CallResult* res) {
     extern __shared__ __align__(16) uint32_t tab_mem[];
-    snappy_encode_frags_loop(src, g, scratch, slot, frag_len, ticket, reinterpret_cast<uint16_t*>(tab_mem));
+    snappy_encode_frags_loop(src, g, scratch, slot, frag_len, ticket, reinterpret_cast<uint16_t*>(tab_mem), in_flag, res);
 }
 __global__ void __launch_bounds__(32) snappy_encode_frags_gtab_kernel(const uint8_t* __restrict__ src, SnappyGeom g,
                                                                       uint8_t* scratch, uint64_t slot, uint32_t* frag_len,
-                                                                      uint32_t* ticket, uint16_t* tables) {
-    snappy_encode_frags_loop(src, g, scratch, slot, frag_len, ticket, tables + (size_t)blockIdx.x * 16384);
+                                                                      uint32_t* ticket, uint16_t* tables,
+                                                                      const uint32_t* in_flag, CallResult* res) {
+    snappy_encode_frags_loop(src, g, scratch, slot, frag_len, ticket, tables + (size_t)blockIdx.x * 16384, in_flag, res);
 }
 
 // Step 2: offsets of every fragment in the final stream, RAP frame and the leading varint

@@ -103,8 +103,9 @@ __device__ __forceinline__ void lz4_put_ext(uint8_t* dst, uint32_t v, int lane) 
 
 template <bool WIDE>
 __device__ inline uint32_t lz4_encode_warp_impl(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, int64_t cap,
-                                                bool emit_tail, uint32_t* tail_len, uint32_t* tab_mem, int lane) {
+                                                bool emit_tail, uint32_t* tail_len, uint32_t* tab_mem, int lane, InGate& gate) {
     Lz4Table<WIDE> tab{tab_mem};
+    gate.wait(n);                                           // this variant does not stream its input
     for (int i = lane; i < 4096; i += 32) tab_mem[i] = 0;   // zeroed table: slot value 0 == position 0
     __syncwarp();
 
@@ -276,10 +277,11 @@ __device__ __forceinline__ Lz4Win lz4_load_win(const uint8_t* src, uint32_t pos)
 
 template <bool WIDE>
 __device__ inline uint32_t lz4_encode_warp_fused(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, int64_t cap,
-                                                 bool emit_tail, uint32_t* tail_len, uint32_t* tab_mem, int lane) {
+                                                 bool emit_tail, uint32_t* tail_len, uint32_t* tab_mem, int lane, InGate& gate) {
     Lz4Table<WIDE> tab{tab_mem};
     for (int i = lane; i < 4096; i += 32) tab_mem[i] = 0;
     __syncwarp();
+    gate.wait(min(n, 64u));
     const bool limited = cap >= 0;
     uint32_t op = 0, anchor = 0;
     bool refused = false;
@@ -303,6 +305,7 @@ __device__ inline uint32_t lz4_encode_warp_fused(const uint8_t* __restrict__ src
                 cur = fwd + incl - my_step; nxt = fwd + incl;
                 valid = nxt <= mfl1;                        // lz4.c:2001
             }
+            gate.wait(min(n, __shfl_sync(kFull, cur, 31) + 32u));   // every window of this round lies below cur[31] + 16
             Lz4Win cw = {0, 0, 0};
             uint32_t h = 0x80000000u | lane;
             if (valid) {
@@ -384,6 +387,7 @@ __device__ inline uint32_t lz4_encode_warp_fused(const uint8_t* __restrict__ src
                 const uint32_t delta = mpos - mcand;
                 uint32_t pb = mpos + 8;
                 for (;;) {
+                    gate.wait(min(n, pb + 144u));
                     const uint32_t pa = pb + 4u * lane;
                     uint32_t c = 0;
                     if (pa < mlimit) {
@@ -441,6 +445,7 @@ __device__ inline uint32_t lz4_encode_warp_fused(const uint8_t* __restrict__ src
         }
     }
     if (refused) return 0;
+    gate.wait(n);                                           // the closing literals are read by this warp or by the stitch
     const uint32_t run = n - anchor;
     if (!emit_tail) { if (tail_len) *tail_len = run; return op; }        // lz4.c:2333-2338
     if (tail_len) *tail_len = 0;
@@ -453,14 +458,14 @@ __device__ inline uint32_t lz4_encode_warp_fused(const uint8_t* __restrict__ src
 }
 
 __device__ inline uint32_t lz4_encode_warp(const uint8_t* src, uint32_t n, uint8_t* dst, int64_t cap, bool emit_tail,
-                                           uint32_t* tail_len, uint32_t* tab_mem, int lane) {
+                                           uint32_t* tail_len, uint32_t* tab_mem, int lane, InGate& gate) {
     if (n == 0) { if (lane == 0) dst[0] = 0; if (tail_len) *tail_len = 0; return 1; }   // lz4.c:2418-2428
 #ifdef LLC_LZ4_ENCODER_SIMPLE
-    if (n >= 65547) return lz4_encode_warp_impl<true>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane);
-    return lz4_encode_warp_impl<false>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane);
+    if (n >= 65547) return lz4_encode_warp_impl<true>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane, gate);
+    return lz4_encode_warp_impl<false>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane, gate);
 #else
-    if (n >= 65547) return lz4_encode_warp_fused<true>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane);
-    return lz4_encode_warp_fused<false>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane);
+    if (n >= 65547) return lz4_encode_warp_fused<true>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane, gate);
+    return lz4_encode_warp_fused<false>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane, gate);
 #endif
 }
 

@@ -45,7 +45,8 @@ GPU_API = ["aocl_gpu_ctx_create", "aocl_gpu_ctx_destroy", "aocl_gpu_ctx_stream",
            "aocl_gpu_compress", "aocl_gpu_decompress", "aocl_gpu_set_lz4_frameless",
            "aocl_gpu_decompress_range_async", "aocl_gpu_decompress_batch_async", "aocl_gpu_compress_batch_async",
            "aocl_gpu_launch_count", "aocl_gpu_set_profiling", "aocl_gpu_profile_count", "aocl_gpu_profile_get",
-           "aocl_gpu_debug_counters"]
+           "aocl_gpu_debug_counters", "aocl_gpu_set_input_watermark", "aocl_gpu_decompress_open_async",
+           "aocl_gpu_decompress_slab_async", "aocl_gpu_decompress_close_async"]
 
 _lib = None
 
@@ -80,6 +81,10 @@ def load() -> C.CDLL:
         "aocl_gpu_set_profiling": (None, [vp, i32]), "aocl_gpu_profile_count": (i32, [vp]),
         "aocl_gpu_profile_get": (C.c_float, [vp, i32, C.c_char_p, i32]),
         "aocl_gpu_debug_counters": (i32, [vp, i32]),
+        "aocl_gpu_set_input_watermark": (None, [vp, vp]),
+        "aocl_gpu_decompress_open_async": (i32, [vp, i32, vp, sz, sz]),
+        "aocl_gpu_decompress_slab_async": (i32, [vp, i32, vp, vp, u32, u32]),
+        "aocl_gpu_decompress_close_async": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)     # AttributeError here == a declared symbol is not exported

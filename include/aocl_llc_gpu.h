@@ -64,6 +64,18 @@ int64_t aocl_gpu_decompress(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in,
  * optOff=1 or one OpenMP thread): 1 = on, 0 = off (default). */
 void aocl_gpu_set_lz4_frameless(aocl_gpu_ctx_t ctx, int32_t on);
 
+/* Streaming input for the NEXT aocl_gpu_compress_async on this context (one-shot).  d_flag points to a
+ * 32-bit watermark in device memory that the caller raises (e.g. with 4-byte H2D copies ordered after
+ * the payload copies on its own copy stream) while the encoder is already running:
+ *   LZ4 RAP frames:  bytes present in EVERY partition (send the input in stripes across partitions:
+ *                    partition i occupies [i*(n/T), (i+1)*(n/T)), T = aocl_gpu_partition_count);
+ *   Snappy:          bytes present from the start of the input.
+ * Raise it to 0xffffffff once everything (including the last partition's n % T extra bytes) is there.
+ * Encoder warps wait on the watermark before they touch input beyond it (with a 64-byte margin, so a
+ * cached sector never straddles it).  This is how aocl_llc_compress overlaps the PCIe transfer of a
+ * host buffer with the encode (reference equivalent: none -- its input is already in host memory). */
+void aocl_gpu_set_input_watermark(aocl_gpu_ctx_t ctx, const uint32_t *d_flag);
+
 /* Decode only RAP partitions [first, first+count) of the stream at d_in into
  * d_out + (sum of decomp_len of partitions < first) - out_origin.  Used to shard one frame
  * across GPUs: each rank passes the same frame header and its own partition range.
@@ -71,6 +83,19 @@ void aocl_gpu_set_lz4_frameless(aocl_gpu_ctx_t ctx, int32_t on);
 int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in, size_t n,
                                         void *d_out, size_t out_cap, uint32_t first, uint32_t count,
                                         uint64_t out_origin);
+
+/* Slab-wise decode of one RAP stream, for callers that overlap the decode with their own transfers
+ * (aocl_llc_decompress does, for host buffers: H2D of slab k+1 | decode of slab k | D2H of slab k-1).
+ *   open : parse + validate the frame at d_in (the header, the entry table and -- Snappy -- the varint
+ *          behind it must already be in HBM) and lay the partitions out in the output;
+ *   slab : decode partitions [first, first+count) to their final offsets in d_out, enqueued on the
+ *          context's stream (order it after the slab's H2D copy with cudaStreamWaitEvent);
+ *   close: fetch the result; aocl_gpu_finish() then returns the stream's total or < 0.
+ * Errors are sticky across slabs. */
+int32_t aocl_gpu_decompress_open_async(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in, size_t n, size_t out_cap);
+int32_t aocl_gpu_decompress_slab_async(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in, void *d_out,
+                                       uint32_t first, uint32_t count);
+int32_t aocl_gpu_decompress_close_async(aocl_gpu_ctx_t ctx);
 
 /* Independent frame-less pages (one LZ4 block / one Snappy stream each), all device
  * resident.  Arrays are device arrays of `count` entries.  status[i] receives bytes
