@@ -442,14 +442,14 @@ __device__ __forceinline__ void lz4_encode_parts_loop(const uint8_t* __restrict_
         __syncwarp();
     }
 }
-__global__ void __launch_bounds__(32) lz4_encode_parts_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
+__global__ void __launch_bounds__(32, 28) lz4_encode_parts_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
                                                               uint8_t* scratch, uint64_t slot, Lz4Rec* rec, uint32_t* ticket,
                                                               const uint32_t* in_flag, CallResult* res) {
     extern __shared__ __align__(16) uint32_t tab_mem[];
     __shared__ uint8_t own_mem[kLeanOwnBytes];
     lz4_encode_parts_loop(src, n, T, scratch, slot, rec, ticket, tab_mem, own_mem, in_flag, res);
 }
-__global__ void __launch_bounds__(32) lz4_encode_parts_gtab_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
+__global__ void __launch_bounds__(32, 28) lz4_encode_parts_gtab_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
                                                                    uint8_t* scratch, uint64_t slot, Lz4Rec* rec,
                                                                    uint32_t* ticket, uint32_t* tables,
                                                                    const uint32_t* in_flag, CallResult* res) {

@@ -44,29 +44,95 @@ struct LeanSrc {
         w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
         so = (uint32_t)(a & 3);
     }
-    // 4 bytes at p
+    // 4 bytes at p (only words that overlap [p, p+4) are touched)
     __device__ __forceinline__ uint32_t u32(uint32_t p) const {
         const uint32_t q = p + so, i = q >> 2, sh = (q & 3u) * 8u;
         const uint32_t w0 = w[i];
         if (sh == 0) return w0;
         return __funnelshift_r(w0, w[i + 1], sh);
     }
-    // 8 bytes at p (reads three aligned words; the third always overlaps [p, p+8) or is the word after
-    // a word that does, so it stays inside the unit's 4-byte-granular allocation plus one word; callers
-    // only use it at positions at least 12 bytes before the end of the unit)
-    __device__ __forceinline__ void u64(uint32_t p, uint32_t& lo, uint32_t& hi) const {
+    // 5 bytes at p: lo = bytes 0..3, b4 = byte 4.  They always lie inside two aligned words.
+    __device__ __forceinline__ void u40(uint32_t p, uint32_t& lo, uint32_t& b4) const {
         const uint32_t q = p + so, i = q >> 2, sh = (q & 3u) * 8u;
-        const uint32_t w0 = w[i], w1 = w[i + 1], w2 = w[i + 2];
+        const uint32_t w0 = w[i], w1 = w[i + 1];
         lo = __funnelshift_r(w0, w1, sh);
-        hi = __funnelshift_r(w1, w2, sh);
+        b4 = (w1 >> sh) & 0xffu;
     }
 };
+
+// What one finished sequence needs to be written out.  Emission is deferred: the next round first issues
+// its table gather and only then writes the previous sequence, so token / literal / offset emission runs
+// in the shadow of that gather instead of in front of it (the gather wait went from 19 % to 4 % of the
+// stall samples).
+struct LeanPending {
+    bool valid, post, from_search;
+    uint32_t anchor, mpos, mcand, mc, eqb, lit;
+};
+
+// Writes the pending sequence at dst + op (lz4.c:2098-2219) and returns false if the limitedOutput checks
+// refuse it (lz4.c:2104-2107, 2177-2204).
+__device__ __forceinline__ bool lean_emit(const LeanPending& q, const uint8_t* __restrict__ src, uint8_t* dst, uint32_t& op,
+                                          bool limited, int64_t cap, int lane) {
+    // backward catch-up, bounded by the anchor and by position 0 (lz4.c:2098); eqb = equal bytes among the 4 before
+    uint32_t back = 0;
+    uint32_t ip = q.mpos, m = q.mcand;
+    if (q.from_search) {
+        const uint32_t bwin = (q.mpos >= 4u && q.mcand >= 4u) ? 4u : 0u;
+        const uint32_t roomb = min(q.mpos - q.anchor, q.mcand);
+        back = min(q.eqb, roomb);
+        ip -= back; m -= back;
+        if ((q.eqb == bwin) && (roomb > bwin)) {            // rare: catch-up longer than the 4 bytes already compared
+            for (;;) {
+                const bool can = (ip > q.anchor + lane) && (m > (uint32_t)lane);
+                const bool eq = can && (src[ip - 1 - lane] == src[m - 1 - lane]);
+                const unsigned ne = __ballot_sync(kFull, !eq);
+                const uint32_t cnt = ne ? (uint32_t)(__ffs(ne) - 1) : 32u;
+                ip -= cnt; m -= cnt; back += cnt;
+                if (cnt < 32) break;
+            }
+        }
+    }
+    const uint32_t ll = ip - q.anchor;
+    const uint32_t code = q.mc + back;                      // match length - 4, counted from the caught-up start
+    if (limited) {
+        const uint32_t ll_ext = ll >= 15 ? (ll - 15) / 255 + 1 : 0;
+        if (q.from_search && (int64_t)op + 1 + ll + 8 + ll / 255 > cap) return false;
+        if ((int64_t)op + 1 + ll_ext + ll + 2 + 6 + (code + 240) / 255 > cap) return false;
+    }
+    if ((ll < 15u) & (code < 15u)) {
+        // whole sequence (token, <= 14 literals, offset) is at most 17 bytes: one byte per lane.
+        // In a post round lane t >= 1 probed position anchor + t - 1, so it already held literal t-1.
+        const uint32_t offv = ip - m;
+        uint32_t v = q.lit;
+        if (!q.post && (uint32_t)(lane - 1) < ll) v = src[q.anchor + lane - 1];
+        if (lane == 0) v = (ll << 4) | code;
+        if ((uint32_t)lane == ll + 1u) v = offv;
+        if ((uint32_t)lane == ll + 2u) v = offv >> 8;
+        if ((uint32_t)lane <= ll + 2u) dst[op + lane] = (uint8_t)v;
+        op += ll + 3u;
+    } else {
+        // ---- token | literal-length bytes | literals | offset | match-length bytes
+        const uint32_t ll_ext = ll >= 15 ? (ll - 15) / 255 + 1 : 0;
+        const uint32_t ml_ext = code >= 15 ? (code - 15) / 255 + 1 : 0;
+        if (lane == 0) dst[op] = (uint8_t)((min(ll, 15u) << 4) | min(code, 15u));
+        if (ll_ext) lz4_put_ext(dst + op + 1, ll - 15, lane);
+        if (ll <= 32) { if ((uint32_t)lane < ll) dst[op + 1 + ll_ext + lane] = src[q.anchor + lane]; }
+        else warp_copy(dst + op + 1 + ll_ext, src + q.anchor, ll, lane);
+        op += 1 + ll_ext + ll;
+        if (lane == 0) { dst[op] = (uint8_t)(ip - m); dst[op + 1] = (uint8_t)((ip - m) >> 8); }
+        op += 2;
+        if (ml_ext) lz4_put_ext(dst + op, code - 15, lane);
+        op += ml_ext;
+    }
+    return true;
+}
 
 __device__ inline uint32_t lz4_encode_warp_lean(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, int64_t cap,
                                                 bool emit_tail, uint32_t* tail_len, uint32_t* tab, uint8_t* own,
                                                 int lane, InGate& gate) {
     const LeanSrc S(src);
     const bool limited = cap >= 0;
+    const bool gated = gate.flag != nullptr;
     uint32_t op = 0, anchor = 0;
     bool refused = false;
 
@@ -81,87 +147,81 @@ __device__ inline uint32_t lz4_encode_warp_lean(const uint8_t* __restrict__ src,
         bool post = false;                                  // lane 0 = insert of base-2, lane 1 = probe of base
         uint32_t base = 0;                                  // post rounds: first position after the match
         uint32_t fwd = 1, step = 1, nb = 64;                // search schedule (lz4.c:1991-1997)
+        LeanPending pend;
+        pend.valid = false;
         for (;;) {
             // ---------------- one round of 32 slots in serial order ----------------
-            uint32_t cur, nxt;
+            uint32_t cur, my_step = 1, bound;
             bool valid, probe = true;
             if (post) {
                 // lane 0: insert base-2 (lz4.c:2230); lane 1: probe of base (lz4.c:2233-2288, always
                 // executed); lane L >= 2: search probe number L-1 at base+L-1, step 1 (lz4.c:1991-2001)
-                cur = base + lane - (lane == 0 ? 0u : 1u) - (lane == 0 ? 2u : 0u);
-                nxt = cur + 1;
+                cur = base + (uint32_t)lane - (lane == 0 ? 2u : 1u);
                 probe = lane != 0;
-                valid = (lane <= 1) || (nxt <= mfl1);
+                valid = (lane <= 1) || (cur < mfl1);        // next position <= mflimitPlusOne
+                bound = base + 31u;
             } else {
-                const uint32_t my_step = (lane == 0) ? step : ((nb + lane - 1) >> 6);
+                my_step = (lane == 0) ? step : ((nb + lane - 1) >> 6);
                 const uint32_t incl = warp_incl_sum(my_step, lane);
-                cur = fwd + incl - my_step; nxt = fwd + incl;
-                valid = nxt <= mfl1;                        // lz4.c:2001
+                cur = fwd + incl - my_step;
+                valid = fwd + incl <= mfl1;                 // lz4.c:2001
+                bound = fwd + 32u * ((nb + 31u) >> 6);
             }
-            gate.wait(min(n, __shfl_sync(kFull, cur, 31) + 96u));
-            uint32_t lo = 0, hi = 0, h = 0, chk = 0, entry = 0;
+            // everything this round reads (probe windows, the 128-byte verify span) lies below bound + 140
+            if (gated) gate.wait(min(n, bound + 256u));
+            uint32_t lo = 0, b4 = 0, h = 0, chk = 0, entry = 0;
             if (valid) {
-                S.u64(cur, lo, hi);
-                h = lz4_hash5((uint64_t)lo | ((uint64_t)hi << 32));
+                S.u40(cur, lo, b4);
+                h = lz4_hash5((uint64_t)lo | ((uint64_t)b4 << 32));
                 chk = lean_check(lo);
                 entry = tab[h];
                 own[h] = (uint8_t)lane;
             }
+            // ---- the previous sequence is written out while the gather is in flight
+            if (pend.valid) {
+                pend.valid = false;
+                if (!lean_emit(pend, src, dst, op, limited, cap, lane)) { refused = true; break; }
+            }
             __syncwarp();
-            const bool clash = valid && own[h] != (uint8_t)lane;
+            const bool clashed = __any_sync(kFull, valid && own[h] != (uint8_t)lane);
             uint32_t cand = entry & kLeanPosMask, cchk = entry >> 19;
-            unsigned peers = 1u << lane;
-            if (__any_sync(kFull, clash)) {                 // two slots of this round share a bucket
+            unsigned peers = 0;
+            if (clashed) {                                  // two slots of this round share a bucket
                 peers = __match_any_sync(kFull, valid ? h : (0x80000000u | (uint32_t)lane));
                 const unsigned before = peers & ((1u << lane) - 1u);
-                const int from = before ? (31 - __clz(before)) : lane;
-                const uint32_t ppos = __shfl_sync(kFull, cur, from), pchk = __shfl_sync(kFull, chk, from);
-                if (before) { cand = ppos; cchk = pchk; }    // that slot would have overwritten the bucket
+                const int f = before ? (31 - __clz(before)) : lane;
+                const uint32_t ppos = __shfl_sync(kFull, cur, f), pchk = __shfl_sync(kFull, chk, f);
+                if (before) { cand = ppos; cchk = pchk; }   // that slot would have overwritten the bucket
             }
             const bool maybe = valid && probe && cchk == chk && cur - cand <= 65535u;   // lz4.c:2048-2057
             unsigned mb = __ballot_sync(kFull, maybe);
             const unsigned inv = __ballot_sync(kFull, !valid);
 
-            // ---------------- first surviving slot: verify, catch up, count ----------------
+            // ---------------- first surviving slot: verify, count ----------------
             int win;
-            bool win_is_match = false, go_b = false;
-            uint32_t mpos = 0, mcand = 0, back = 0, mc = 0;
+            bool win_is_match = false;
+            uint32_t mpos = 0, mcand = 0, mc = 0, eqb = 0;
             for (;;) {
                 const unsigned events = mb | inv;
                 win = events ? (__ffs(events) - 1) : 32;
-                if (win >= 32 || !((mb >> win) & 1u)) break;
+                if (!((mb >> (win & 31)) & 1u) || win >= 32) break;
                 mpos = __shfl_sync(kFull, cur, win);
                 mcand = __shfl_sync(kFull, cand, win);
                 const uint32_t delta = mpos - mcand;
-                const bool from_search = !(post && win == 1);
-                gate.wait(min(n, mpos + 192u));
-                // lane j looks at bytes [4j-4, 4j) relative to the two positions
+                // lane j looks at bytes [4j-4, 4j) relative to the two positions: lane 0 the catch-up bytes
+                // (lz4.c:2098), lane 1 the four bytes the reference verifies, lanes 2..31 the next 120 (LZ4_count)
+                const uint32_t pa = mpos + 4u * (uint32_t)lane - 4u;
+                const bool look = lane == 0 ? (!(post && win == 1) && mpos >= 4u && mcand >= 4u) : (lane == 1 || pa < mlimit);
                 uint32_t c = 0;                             // equal bytes in this lane's word
-                if (lane == 0) {
-                    if (from_search && mpos >= 4u && mcand >= 4u) {
-                        const uint32_t x = S.u32(mpos - 4u) ^ S.u32(mcand - 4u);
-                        c = x ? ((uint32_t)__clz(x) >> 3) : 4u;
-                    }
-                } else {
-                    const uint32_t pa = mpos + 4u * (uint32_t)(lane - 1);
-                    if (lane == 1 || pa < mlimit) {
-                        const uint32_t x = S.u32(pa) ^ S.u32(pa - delta);
-                        c = x ? ((uint32_t)(__ffs(x) - 1) >> 3) : 4u;
-                        if (lane != 1) c = min(c, mlimit - pa);
-                    }
+                if (look) {
+                    const uint32_t x = S.u32(pa) ^ S.u32(pa - delta);
+                    c = (uint32_t)__clz(lane == 0 ? x : __brev(x)) >> 3;     // from the top for lane 0, from the bottom otherwise
+                    if (lane >= 2) c = min(c, mlimit - pa);
                 }
                 const unsigned part = __ballot_sync(kFull, c < 4u);
-                if (part & 2u) { mb &= ~(1u << win); continue; }   // check collision: not a match
+                if (part & 2u) { mb &= ~(1u << win); continue; }   // 13-bit check collision: not a match
                 win_is_match = true;
-                // backward, bounded by the anchor and by position 0 (lz4.c:2098)
-                back = 0; go_b = false;
-                if (from_search) {
-                    const uint32_t bwin = (mpos >= 4u && mcand >= 4u) ? 4u : 0u;
-                    const uint32_t eqb = __shfl_sync(kFull, c, 0);
-                    const uint32_t roomb = min(mpos - anchor, mcand);
-                    back = min(eqb, roomb);
-                    go_b = (eqb == bwin) && (roomb > bwin);
-                }
+                eqb = __shfl_sync(kFull, c, 0);
                 // forward: lanes 2..31 hold bytes +4 .. +123
                 const unsigned fpart = part & ~3u;
                 if (fpart) {
@@ -172,12 +232,11 @@ __device__ inline uint32_t lz4_encode_warp_lean(const uint8_t* __restrict__ src,
                     uint32_t pb = mpos + 124u;
                     for (;;) {
                         gate.wait(min(n, pb + 208u));
-                        const uint32_t pa = pb + 4u * lane;
+                        const uint32_t pc = pb + 4u * lane;
                         uint32_t cc = 0;
-                        if (pa < mlimit) {
-                            const uint32_t x = S.u32(pa) ^ S.u32(pa - delta);
-                            cc = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
-                            cc = min(cc, mlimit - pa);
+                        if (pc < mlimit) {
+                            const uint32_t x = S.u32(pc) ^ S.u32(pc - delta);
+                            cc = min((uint32_t)__clz(__brev(x)) >> 3, mlimit - pc);
                         }
                         const unsigned partial = __ballot_sync(kFull, cc < 4);
                         if (partial) {
@@ -192,71 +251,33 @@ __device__ inline uint32_t lz4_encode_warp_lean(const uint8_t* __restrict__ src,
             }
 
             // ---------------- commit the table writes the serial algorithm would have made ----------------
-            const unsigned commit = (win_is_match ? (win == 31 ? kFull : ((2u << win) - 1u))
-                                                  : (win == 0 ? 0u : (win >= 32 ? kFull : ((1u << win) - 1u))));
-            if (valid && ((commit >> lane) & 1u)) {
-                const unsigned mine = peers & commit;
-                if ((31 - __clz(mine)) == lane) tab[h] = cur | (chk << 19);
+            // slots up to the winning match, or up to (not including) the slot that ran into the end of the block
+            const int limit = win_is_match ? win : win - 1;
+            bool wr = valid && lane <= limit;
+            if (clashed && wr) {                            // last writer per bucket
+                const unsigned upto = limit >= 31 ? kFull : ((2u << limit) - 1u);
+                const unsigned later = lane >= 31 ? 0u : (peers & upto & ~((2u << lane) - 1u));
+                if (later) wr = false;
             }
+            if (wr) tab[h] = cur | (chk << 19);
             __syncwarp();
             if (win >= 32) {                                // nothing happened: next 32 probes of the same search
                 if (post) { fwd = base + 31; step = 1; nb = 64 + 30; post = false; }
-                else { fwd = __shfl_sync(kFull, nxt, 31); step = (nb + 31) >> 6; nb += 32; }
+                else { fwd = __shfl_sync(kFull, cur + my_step, 31); step = (nb + 31) >> 6; nb += 32; }
                 continue;
             }
             if (!win_is_match) break;                       // search ran into the end of the block -> closing literals
 
-            // ---------------- the match ----------------
-            uint32_t ip = mpos - back, m = mcand - back;
-            if (go_b) {                                     // rare: catch-up longer than 4 bytes
-                for (;;) {
-                    const bool can = (ip > anchor + lane) && (m > (uint32_t)lane);
-                    const bool eq = can && (src[ip - 1 - lane] == src[m - 1 - lane]);
-                    const unsigned ne = __ballot_sync(kFull, !eq);
-                    const uint32_t cnt = ne ? (uint32_t)(__ffs(ne) - 1) : 32u;
-                    ip -= cnt; m -= cnt; back += cnt;
-                    if (cnt < 32) break;
-                }
-            }
-            const bool from_search = !(post && win == 1);
-            const uint32_t ll = ip - anchor;
-            const uint32_t code = mc + back;                // match length - 4, counted from the caught-up start
-            // ---- emit: token | literal-length bytes | literals | offset | match-length bytes
-            const uint32_t ll_ext = ll >= 15 ? (ll - 15) / 255 + 1 : 0;
-            const uint32_t ml_ext = code >= 15 ? (code - 15) / 255 + 1 : 0;
-            if (limited) {
-                // lz4.c:2104-2107 (literals) and lz4.c:2177-2204 (match length)
-                if (from_search && (int64_t)op + 1 + ll + 8 + ll / 255 > cap) { refused = true; break; }
-                if ((int64_t)op + 1 + ll_ext + ll + 2 + 6 + (code + 240) / 255 > cap) { refused = true; break; }
-            }
-            if ((ll < 15u) & (code < 15u)) {
-                // whole sequence (token, <= 14 literals, offset) is at most 17 bytes: one byte per lane.
-                // In a post round lane t >= 1 probed position anchor + t - 1, so it already holds literal t-1.
-                const uint32_t offv = ip - m;
-                uint32_t v = lo & 0xffu;
-                if (!post && lane >= 1 && (uint32_t)lane <= ll) v = src[anchor + lane - 1];
-                if (lane == 0) v = (ll << 4) | code;
-                if ((uint32_t)lane == ll + 1u) v = offv & 0xffu;
-                if ((uint32_t)lane == ll + 2u) v = offv >> 8;
-                if ((uint32_t)lane <= ll + 2u) dst[op + lane] = (uint8_t)v;
-                op += ll + 3u;
-            } else {
-                if (lane == 0) dst[op] = (uint8_t)((min(ll, 15u) << 4) | min(code, 15u));
-                if (ll_ext) lz4_put_ext(dst + op + 1, ll - 15, lane);
-                if (ll <= 32) { if ((uint32_t)lane < ll) dst[op + 1 + ll_ext + lane] = src[anchor + lane]; }
-                else warp_copy(dst + op + 1 + ll_ext, src + anchor, ll, lane);
-                op += 1 + ll_ext + ll;
-                if (lane == 0) { dst[op] = (uint8_t)(ip - m); dst[op + 1] = (uint8_t)((ip - m) >> 8); }
-                op += 2;
-                if (ml_ext) lz4_put_ext(dst + op, code - 15, lane);
-                op += ml_ext;
-            }
-
+            // ---------------- the match: remember it, move on ----------------
+            pend.valid = true; pend.post = post; pend.from_search = !(post && win == 1);
+            pend.anchor = anchor; pend.mpos = mpos; pend.mcand = mcand; pend.mc = mc; pend.eqb = eqb;
+            pend.lit = lo & 0xffu;
             base = mpos + 4 + mc;                           // first position after the match
             anchor = base;
             if (base >= mfl1) break;                        // lz4.c:2227
             post = true;
         }
+        if (pend.valid && !refused && !lean_emit(pend, src, dst, op, limited, cap, lane)) refused = true;
     }
     if (refused) return 0;
     gate.wait(n);                                           // the closing literals are read by this warp or by the stitch

@@ -14,7 +14,8 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # aocl-compression_b200/
 REPO_ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libaocl_compression.so")
+# AOCL_LLC_LIB points experiments at an A/B build of the same sources (make ... LIB=lib_x); the product is lib/
+LIB_PATH = os.environ.get("AOCL_LLC_LIB") or os.path.join(PKG_DIR, "lib", "libaocl_compression.so")
 
 LZ4, SNAPPY = 0, 4
 CODEC_NAMES = {LZ4: "lz4", SNAPPY: "snappy"}

@@ -219,6 +219,7 @@ def run_b200(args, wl):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
+    os.environ.setdefault("AOCL_GPU_DEVICE", str(local))     # the aocl_llc_* host API opens its context on this rank's GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -306,7 +307,20 @@ def run_b200(args, wl):
     enc_name = "lz4_encode_parts_kernel" if codec == LZ4 else "snappy_encode_frags_kernel"
     dom_name = max(kern, key=lambda k: kern[k])
     dom_ms = kern[dom_name]
-    dec_ms = kern.get("decode_parts_kernel", td)
+    dec_name = next((k for k in kern if "decode_parts" in k), "decode_parts_kernel")
+    dec_ms = kern.get(dec_name, td)
+    # DRAM traffic of the same kernels from the committed `ncu --set full` captures (profiles/traffic.json)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+    except Exception:
+        pass
+
+    def traffic_of(name):
+        for key, val in traffic.items():
+            if key in name:
+                return val
+        return None
 
     # ---- end to end through the reference-facing API with pinned host buffers
     e2e = None
@@ -319,19 +333,21 @@ def run_b200(args, wl):
         d.optOff, d.optLevel, d.measureStats = 0, -1, 1
         assert L.aocl_llc_setup(C.byref(d), codec) == 0
         e2e_steps = max(1, min(args.steps, 5))
-        tot = 0.0
+        tot = tot_c = 0.0
         for it in range(1 + e2e_steps):
             if dist is not None:
                 dist.barrier()
             t0 = time.perf_counter()
             d.inBuf, d.inSize, d.outBuf, d.outSize = h_in.data_ptr(), U, h_comp.data_ptr(), cap
             c2 = L.aocl_llc_compress(C.byref(d), codec)
+            t1 = time.perf_counter()
             assert c2 == csz, (c2, csz)
             d.inBuf, d.inSize, d.outBuf, d.outSize = h_comp.data_ptr(), c2, h_back.data_ptr(), U
             r2 = L.aocl_llc_decompress(C.byref(d), codec)
             assert r2 == U, r2
             if it >= 1:
                 tot += time.perf_counter() - t0
+                tot_c += t1 - t0
         assert torch.equal(h_back, h_in), "e2e round trip mismatch"
         e2e_s = tot / e2e_steps
         if dist is not None:
@@ -340,7 +356,9 @@ def run_b200(args, wl):
             e2e_s = float(t.item())
         e2e = {"value": world * 2 * U / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": U + csz,
                "d2h_bytes_per_step": csz + U, "ms_per_step": e2e_s * 1e3,
-               "api": "aocl_llc_compress + aocl_llc_decompress, pinned host buffers"}
+               "compress_ms": tot_c / e2e_steps * 1e3, "decompress_ms": (tot - tot_c) / e2e_steps * 1e3,
+               "api": "aocl_llc_compress + aocl_llc_decompress, pinned host buffers; transfers pipelined with the kernels "
+                      "(striped H2D behind an input watermark / slab-wise H2D-decode-D2H)"}
 
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample (rank 0, N=1)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -367,8 +385,8 @@ def run_b200(args, wl):
                        "kernels_ms": {k: round(v, 4) for k, v in kern.items()}},
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": alg_bytes / (dom_ms / 1e3) / 1e9,
                          "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (dom_ms / 1e3) / 1e9 / hbm_peak,
-                         "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes": int(alg_bytes)},
-            "roofline_decompress": {"bound": "hbm", "kernel": "decode_parts_kernel",
+                         "traffic": traffic_of(dom_name), "peak_kind": peak_kind, "algorithmic_bytes": int(alg_bytes)},
+            "roofline_decompress": {"bound": "hbm", "kernel": dec_name, "traffic": traffic_of(dec_name),
                                     "achieved": alg_bytes / (dec_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                     "frac": alg_bytes / (dec_ms / 1e3) / 1e9 / hbm_peak, "peak_kind": peak_kind,
                                     "user_GBps": U / (dec_ms / 1e3) / 1e9},
