@@ -14,6 +14,7 @@
 // Pageable buffers and small calls take the plain copy - run - copy sequence.
 #include "../../include/aocl_llc.h"
 #include "../../include/aocl_llc_gpu.h"
+#include "../../include/aocl_llc_native.h"
 
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -345,4 +346,72 @@ extern "C" int32_t aocl_skip_rap_frame_mt(char* src, int32_t src_size) {
     if (magic != kRapMagic) return 0;
     uint32_t frame; memcpy(&frame, head + 8, 4);
     return (int32_t)frame;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The codecs' native C entry points (include/aocl_llc_native.h), thin shims over run_codec().
+// ------------------------------------------------------------------------------------------------
+extern "C" int LZ4_compressBound(int n) {                      // LZ4_COMPRESSBOUND, lz4.h:258-287
+    return (unsigned)n > 0x7E000000u ? 0 : n + n / 255 + 16;
+}
+
+extern "C" int LZ4_compress_default(const char* src, char* dst, int src_size, int dst_cap) {
+    if (src_size < 0 || dst_cap <= 0) return 0;
+    const int64_t r = run_codec(true, (int)LZ4, const_cast<char*>(src), (size_t)src_size, dst, (size_t)dst_cap);
+    return r > 0 && r <= 0x7fffffff ? (int)r : 0;               // 0 = failure (lz4.h:196-203)
+}
+
+extern "C" int LZ4_decompress_safe(const char* src, char* dst, int csize, int dst_cap) {
+    if (csize < 0 || dst_cap < 0) return -1;
+    const int64_t r = run_codec(false, (int)LZ4, const_cast<char*>(src), (size_t)csize, dst, (size_t)dst_cap);
+    return r >= 0 && r <= 0x7fffffff ? (int)r : -1;             // negative = malformed (lz4.h:222-232)
+}
+
+extern "C" size_t snappy_max_compressed_length(size_t n) { return 32 + n + n / 6; }   // snappy.cc:160-182
+
+// varint32 of the uncompressed length; frame-aware (snappy.cc:596-615)
+static bool snappy_length_of(const char* p, size_t n, size_t* out) {
+    if (!p || !out) return false;
+    unsigned char head[16 + 5] = {0};
+    size_t skip = 0;
+    if (n >= 16) {
+        if (on_device(p)) { if (cudaMemcpy(head, p, 16, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return false; } }
+        else memcpy(head, p, 16);
+        uint64_t magic; memcpy(&magic, head, 8);
+        if (magic == kRapMagic) { skip = rd32(head + 8); if (skip > n) return false; }
+    }
+    const size_t take = n - skip < 5 ? n - skip : 5;
+    if (on_device(p)) { if (take && cudaMemcpy(head, p + skip, take, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return false; } }
+    else memcpy(head, p + skip, take);
+    uint32_t v = 0;
+    for (size_t i = 0; i < take; i++) {                         // Varint::Parse32WithLimit, snappy-stubs-internal.h:440-470
+        const uint32_t b = head[i];
+        if (i == 4 && b > 15) return false;
+        v |= (b & 127u) << (7 * i);
+        if (b < 128) { *out = v; return true; }
+    }
+    return false;
+}
+
+extern "C" snappy_status snappy_uncompressed_length(const char* compressed, size_t n, size_t* result) {
+    return snappy_length_of(compressed, n, result) ? SNAPPY_OK : SNAPPY_INVALID_INPUT;
+}
+
+extern "C" snappy_status snappy_compress(const char* input, size_t n, char* compressed, size_t* compressed_length) {
+    if (!compressed_length) return SNAPPY_INVALID_INPUT;
+    if (*compressed_length < snappy_max_compressed_length(n)) return SNAPPY_BUFFER_TOO_SMALL;   // snappy-c.cc:38-40
+    const int64_t r = run_codec(true, (int)SNAPPY, const_cast<char*>(input), n, compressed, *compressed_length);
+    if (r < 0) return SNAPPY_INVALID_INPUT;
+    *compressed_length = (size_t)r;
+    return SNAPPY_OK;
+}
+
+extern "C" snappy_status snappy_uncompress(const char* compressed, size_t n, char* uncompressed, size_t* uncompressed_length) {
+    size_t real = 0;
+    if (!uncompressed_length || !snappy_length_of(compressed, n, &real)) return SNAPPY_INVALID_INPUT;
+    if (*uncompressed_length < real) return SNAPPY_BUFFER_TOO_SMALL;                            // snappy-c.cc:55-57
+    const int64_t r = run_codec(false, (int)SNAPPY, const_cast<char*>(compressed), n, uncompressed, *uncompressed_length);
+    if (r < 0 || (size_t)r != real) return SNAPPY_INVALID_INPUT;
+    *uncompressed_length = real;
+    return SNAPPY_OK;
 }

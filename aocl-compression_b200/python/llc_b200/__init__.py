@@ -41,6 +41,8 @@ class AoclDesc(C.Structure):
 
 HOST_API = ["aocl_llc_compress", "aocl_llc_decompress", "aocl_llc_setup", "aocl_llc_destroy", "aocl_llc_version",
             "aocl_get_rap_frame_bound_mt", "aocl_skip_rap_frame_mt"]
+NATIVE_API = ["LZ4_compressBound", "LZ4_compress_default", "LZ4_decompress_safe", "snappy_compress", "snappy_uncompress",
+              "snappy_max_compressed_length", "snappy_uncompressed_length"]
 GPU_API = ["aocl_gpu_ctx_create", "aocl_gpu_ctx_destroy", "aocl_gpu_ctx_stream", "aocl_gpu_partition_count",
            "aocl_gpu_compress_bound", "aocl_gpu_compress_async", "aocl_gpu_decompress_async", "aocl_gpu_finish",
            "aocl_gpu_compress", "aocl_gpu_decompress", "aocl_gpu_set_lz4_frameless",
@@ -82,6 +84,13 @@ def load() -> C.CDLL:
         "aocl_gpu_set_profiling": (None, [vp, i32]), "aocl_gpu_profile_count": (i32, [vp]),
         "aocl_gpu_profile_get": (C.c_float, [vp, i32, C.c_char_p, i32]),
         "aocl_gpu_debug_counters": (i32, [vp, i32]),
+        "LZ4_compressBound": (C.c_int, [C.c_int]),
+        "LZ4_compress_default": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "LZ4_decompress_safe": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "snappy_compress": (C.c_int, [vp, sz, vp, C.POINTER(sz)]),
+        "snappy_uncompress": (C.c_int, [vp, sz, vp, C.POINTER(sz)]),
+        "snappy_max_compressed_length": (sz, [sz]),
+        "snappy_uncompressed_length": (C.c_int, [vp, sz, C.POINTER(sz)]),
         "aocl_gpu_set_input_watermark": (None, [vp, vp]),
         "aocl_gpu_decompress_open_async": (i32, [vp, i32, vp, sz, sz]),
         "aocl_gpu_decompress_slab_async": (i32, [vp, i32, vp, vp, u32, u32]),

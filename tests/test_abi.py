@@ -32,6 +32,19 @@ def test_every_declared_symbol_is_exported(lib):
     for n in names:
         assert hasattr(lib, n), n
     assert set(llc_b200.HOST_API) <= set(names) and set(llc_b200.GPU_API) <= set(names)
+    # the codecs' native entry points (include/aocl_llc_native.h)
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "aocl_llc_native.h")).read(), flags=re.S)
+    native = sorted(set(re.findall(r"\b((?:LZ4|snappy)_[A-Za-z0-9_]+)\s*\(", text)))
+    assert native == sorted(llc_b200.NATIVE_API)
+    for n in native:
+        assert hasattr(lib, n), n
+
+
+def test_native_bounds_without_gpu(lib):
+    assert lib.LZ4_compressBound(65025) == 65296               # lz4_gtest.cpp:323-326
+    assert lib.LZ4_compressBound(0x7E000001) == 0
+    for n, want in ((0, 32), (1, 33), (6, 39), (100, 148), (65536, 76490)):   # snappy.cc:160-182
+        assert lib.snappy_max_compressed_length(n) == want
 
 
 def test_descriptor_layout_matches_reference():

@@ -57,3 +57,41 @@ def test_round_trip_large(gpu_lib, oracle, corpus, codec):
     assert r2 == len(data) and back == data.tobytes()
     # the oracle decoder accepts the GPU stream as well
     assert oracle.decompress(stream, codec, len(data)) == data.tobytes()
+
+
+def test_native_entry_points(oracle, corpus):
+    """LZ4_* / snappy_* shims (include/aocl_llc_native.h): same streams as the unified API, reference return conventions."""
+    import ctypes as C
+    import llc_b200
+    L = llc_b200.load()
+    data = np.ascontiguousarray(corpus["text"][:700001])
+    n = len(data)
+    # LZ4
+    want = oracle.compress(data, ol.LZ4)
+    cap = L.LZ4_compressBound(n) + 16 + 12 * 8192
+    dst = np.zeros(cap, dtype=np.uint8)
+    r = L.LZ4_compress_default(data.ctypes.data, dst.ctypes.data, n, cap)
+    assert r == len(want) and dst[:r].tobytes() == want
+    back = np.zeros(n, dtype=np.uint8)
+    assert L.LZ4_decompress_safe(dst.ctypes.data, back.ctypes.data, r, n) == n and back.tobytes() == data.tobytes()
+    bad = dst[:r].copy(); bad[40:60] = 0xFF
+    assert L.LZ4_decompress_safe(bad.ctypes.data, back.ctypes.data, r, n) != n or back.tobytes() != data.tobytes()
+    assert L.LZ4_compress_default(data.ctypes.data, dst.ctypes.data, n, 100) == 0      # does not fit -> 0
+    # Snappy
+    want = oracle.compress(data, ol.SNAPPY)
+    cap = L.snappy_max_compressed_length(n)
+    dst = np.zeros(cap, dtype=np.uint8)
+    clen = C.c_size_t(cap - 1)
+    assert L.snappy_compress(data.ctypes.data, n, dst.ctypes.data, C.byref(clen)) == 2  # SNAPPY_BUFFER_TOO_SMALL
+    clen = C.c_size_t(cap)
+    assert L.snappy_compress(data.ctypes.data, n, dst.ctypes.data, C.byref(clen)) == 0
+    assert clen.value == len(want) and dst[:clen.value].tobytes() == want
+    ulen = C.c_size_t(0)
+    assert L.snappy_uncompressed_length(dst.ctypes.data, clen.value, C.byref(ulen)) == 0 and ulen.value == n
+    back = np.zeros(n, dtype=np.uint8)
+    ulen = C.c_size_t(n - 1)
+    assert L.snappy_uncompress(dst.ctypes.data, clen.value, back.ctypes.data, C.byref(ulen)) == 2
+    ulen = C.c_size_t(n)
+    assert L.snappy_uncompress(dst.ctypes.data, clen.value, back.ctypes.data, C.byref(ulen)) == 0
+    assert ulen.value == n and back.tobytes() == data.tobytes()
+    assert L.snappy_uncompress(dst[3:].ctypes.data, 5, back.ctypes.data, C.byref(ulen)) == 1   # SNAPPY_INVALID_INPUT
