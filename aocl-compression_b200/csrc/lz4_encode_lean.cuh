@@ -103,7 +103,7 @@ __device__ __forceinline__ bool lean_emit(const LeanPending& q, const uint8_t* _
         // whole sequence (token, <= 14 literals, offset) is at most 17 bytes: one byte per lane.
         // In a post round lane t >= 1 probed position anchor + t - 1, so it already held literal t-1.
         const uint32_t offv = ip - m;
-        uint32_t v = q.lit;
+        uint32_t v = q.lit;                                  // post rounds: already the byte this lane writes
         if (!q.post && (uint32_t)(lane - 1) < ll) v = src[q.anchor + lane - 1];
         if (lane == 0) v = (ll << 4) | code;
         if ((uint32_t)lane == ll + 1u) v = offv;
@@ -123,6 +123,74 @@ __device__ __forceinline__ bool lean_emit(const LeanPending& q, const uint8_t* _
         op += 2;
         if (ml_ext) lz4_put_ext(dst + op, code - 15, lane);
         op += ml_ext;
+    }
+    return true;
+}
+
+// Verification of one candidate, split in two so that other work can be placed between the loads and their
+// first use.  Lane j looks at bytes [4j-4, 4j) relative to the two positions: lane 0 the catch-up bytes
+// (lz4.c:2098), lane 1 the four bytes the reference verifies (lz4.c:2048-2057), lanes 2..30 the next 116
+// (LZ4_count, lz4.c:656-679).
+struct LeanProbe { uint32_t xa, xb, pa; bool look; };
+__device__ __forceinline__ LeanProbe lean_verify_issue(const LeanSrc& S, uint32_t mpos, uint32_t mcand, bool from_search,
+                                                       uint32_t mlimit, uint32_t n, int lane) {
+    LeanProbe v;
+    v.pa = mpos + 4u * (uint32_t)lane - 4u;
+    if (mpos >= 4u && mcand >= 4u) {
+        // The 32 lanes read 128 contiguous bytes of each stream: one aligned word per lane, the following
+        // word comes from the next lane.  Lane 31 has no next lane; it does not take part (see finish).
+        const uint32_t qa = S.so + mpos - 4u, qb = S.so + mcand - 4u;
+        const uint32_t ia = (qa >> 2) + (uint32_t)lane, ib = (qb >> 2) + (uint32_t)lane;
+        const uint32_t last = (S.so + n - 1u) >> 2;         // last aligned word that holds bytes of the unit
+        const uint32_t wa = ia <= last ? S.w[ia] : 0u, wb = ib <= last ? S.w[ib] : 0u;
+        const uint32_t wa1 = __shfl_down_sync(kFull, wa, 1), wb1 = __shfl_down_sync(kFull, wb, 1);
+        v.xa = __funnelshift_r(wa, wa1, (qa & 3u) * 8u);
+        v.xb = __funnelshift_r(wb, wb1, (qb & 3u) * 8u);
+        v.look = lane == 0 ? from_search : (lane == 1 || (lane < 31 && v.pa < mlimit));
+    } else {                                                // within 4 bytes of the start of the unit: per-lane loads
+        v.look = lane == 0 ? false : (lane == 1 || (lane < 31 && v.pa < mlimit));
+        v.xa = v.xb = 0;
+        if (v.look) { v.xa = S.u32(v.pa); v.xb = S.u32(v.pa - (mpos - mcand)); }
+    }
+    return v;
+}
+// Returns false on a 13-bit check collision (the four bytes differ).  mc = equal bytes after the first four,
+// eqb = equal bytes among the four before the two positions.
+__device__ __forceinline__ bool lean_verify_finish(const LeanSrc& S, const LeanProbe& v, uint32_t mpos, uint32_t mcand,
+                                                   uint32_t mlimit, uint32_t n, int lane, InGate& gate, uint32_t& mc, uint32_t& eqb) {
+    uint32_t c = 0;                                         // equal bytes in this lane's word
+    if (v.look) {
+        const uint32_t x = v.xa ^ v.xb;
+        c = (uint32_t)__clz(lane == 0 ? x : __brev(x)) >> 3;             // from the top for lane 0, from the bottom otherwise
+        if (lane >= 2) c = min(c, mlimit - v.pa);
+    }
+    const unsigned part = __ballot_sync(kFull, c < 4u);
+    if (part & 2u) return false;
+    eqb = __shfl_sync(kFull, c, 0);
+    const unsigned fpart = part & 0x7ffffffcu;             // lanes 2..30 hold bytes +4 .. +119
+    if (fpart) {
+        const int first = __ffs(fpart) - 1;
+        mc = 4u * (uint32_t)(first - 2) + __shfl_sync(kFull, c, first);
+    } else {                                                // longer than 120: 128 bytes per extra round
+        const uint32_t delta = mpos - mcand;
+        mc = 116;
+        uint32_t pb = mpos + 120u;
+        for (;;) {
+            gate.wait(min(n, pb + 208u));
+            const uint32_t pc = pb + 4u * lane;
+            uint32_t cc = 0;
+            if (pc < mlimit) {
+                const uint32_t x = S.u32(pc) ^ S.u32(pc - delta);
+                cc = min((uint32_t)__clz(__brev(x)) >> 3, mlimit - pc);
+            }
+            const unsigned partial = __ballot_sync(kFull, cc < 4);
+            if (partial) {
+                const int first = __ffs(partial) - 1;
+                mc += 4u * first + __shfl_sync(kFull, cc, first);
+                break;
+            }
+            mc += 128; pb += 128;
+        }
     }
     return true;
 }
@@ -149,7 +217,8 @@ __device__ inline uint32_t lz4_encode_warp_lean(const uint8_t* __restrict__ src,
         uint32_t fwd = 1, step = 1, nb = 64;                // search schedule (lz4.c:1991-1997)
         LeanPending pend;
         pend.valid = false;
-        for (;;) {
+        bool finished = false;
+        while (!finished) {
             // ---------------- one round of 32 slots in serial order ----------------
             uint32_t cur, my_step = 1, bound;
             bool valid, probe = true;
@@ -196,86 +265,64 @@ __device__ inline uint32_t lz4_encode_warp_lean(const uint8_t* __restrict__ src,
             const bool maybe = valid && probe && cchk == chk && cur - cand <= 65535u;   // lz4.c:2048-2057
             unsigned mb = __ballot_sync(kFull, maybe);
             const unsigned inv = __ballot_sync(kFull, !valid);
+            const uint32_t lit = lo & 0xffu;
 
-            // ---------------- first surviving slot: verify, count ----------------
-            int win;
-            bool win_is_match = false;
-            uint32_t mpos = 0, mcand = 0, mc = 0, eqb = 0;
+            // ---------------- sequences of this round ----------------
+            // A post round whose 32 slots hit 32 different buckets (no clash) keeps going after a match: the
+            // slots behind the match are the insert / probe / search slots of the NEXT sequence, their table
+            // entries are already here and cannot have been touched by the slots committed so far.  So one
+            // gather serves every sequence that starts inside the 32-position window (2-3 for text).
+            unsigned wmask = post ? 1u : 0u;                // slots whose table write is committed (lane 0: insert of base-2)
+            int s_lane = post ? 1 : 0;                      // slot of the current sequence's first probe
+            bool next_post = false;
             for (;;) {
-                const unsigned events = mb | inv;
-                win = events ? (__ffs(events) - 1) : 32;
-                if (!((mb >> (win & 31)) & 1u) || win >= 32) break;
-                mpos = __shfl_sync(kFull, cur, win);
-                mcand = __shfl_sync(kFull, cand, win);
-                const uint32_t delta = mpos - mcand;
-                // lane j looks at bytes [4j-4, 4j) relative to the two positions: lane 0 the catch-up bytes
-                // (lz4.c:2098), lane 1 the four bytes the reference verifies, lanes 2..31 the next 120 (LZ4_count)
-                const uint32_t pa = mpos + 4u * (uint32_t)lane - 4u;
-                const bool look = lane == 0 ? (!(post && win == 1) && mpos >= 4u && mcand >= 4u) : (lane == 1 || pa < mlimit);
-                uint32_t c = 0;                             // equal bytes in this lane's word
-                if (look) {
-                    const uint32_t x = S.u32(pa) ^ S.u32(pa - delta);
-                    c = (uint32_t)__clz(lane == 0 ? x : __brev(x)) >> 3;     // from the top for lane 0, from the bottom otherwise
-                    if (lane >= 2) c = min(c, mlimit - pa);
+                const unsigned scope = ~((1u << s_lane) - 1u);
+                const unsigned events = (mb | inv) & scope;
+                const int win = events ? (__ffs(events) - 1) : 32;
+                if (win >= 32) {                            // no event: the search goes on in the next round
+                    wmask |= scope;
+                    if (post) { fwd = base + 31u; step = 1; nb = 64u + 31u - (uint32_t)s_lane; post = false; }
+                    else { fwd = __shfl_sync(kFull, cur + my_step, 31); step = (nb + 31) >> 6; nb += 32; }
+                    break;
                 }
-                const unsigned part = __ballot_sync(kFull, c < 4u);
-                if (part & 2u) { mb &= ~(1u << win); continue; }   // 13-bit check collision: not a match
-                win_is_match = true;
-                eqb = __shfl_sync(kFull, c, 0);
-                // forward: lanes 2..31 hold bytes +4 .. +123
-                const unsigned fpart = part & ~3u;
-                if (fpart) {
-                    const int first = __ffs(fpart) - 1;
-                    mc = 4u * (uint32_t)(first - 2) + __shfl_sync(kFull, c, first);
-                } else {                                    // longer than 124: 128 bytes per extra round
-                    mc = 120;
-                    uint32_t pb = mpos + 124u;
-                    for (;;) {
-                        gate.wait(min(n, pb + 208u));
-                        const uint32_t pc = pb + 4u * lane;
-                        uint32_t cc = 0;
-                        if (pc < mlimit) {
-                            const uint32_t x = S.u32(pc) ^ S.u32(pc - delta);
-                            cc = min((uint32_t)__clz(__brev(x)) >> 3, mlimit - pc);
-                        }
-                        const unsigned partial = __ballot_sync(kFull, cc < 4);
-                        if (partial) {
-                            const int first = __ffs(partial) - 1;
-                            mc += 4u * first + __shfl_sync(kFull, cc, first);
-                            break;
-                        }
-                        mc += 128; pb += 128;
-                    }
+                const unsigned upto_win = scope & ((2u << win) - 1u);     // slots s_lane .. win   (win <= 31)
+                if (!((mb >> win) & 1u)) {                  // the search ran into the end of the block -> closing literals
+                    wmask |= upto_win & ~(1u << win);
+                    finished = true;
+                    break;
                 }
-                break;
+                const uint32_t mpos = __shfl_sync(kFull, cur, win);
+                const uint32_t mcand = __shfl_sync(kFull, cand, win);
+                const bool from_search = !(post && win == s_lane);      // the probe right after a match takes no catch-up
+                const LeanProbe vp = lean_verify_issue(S, mpos, mcand, from_search, mlimit, n, lane);
+                // ---- the sequence before this one is written out while the verify loads are in flight
+                if (pend.valid) {
+                    pend.valid = false;
+                    if (!lean_emit(pend, src, dst, op, limited, cap, lane)) { refused = true; finished = true; break; }
+                }
+                uint32_t mc = 0, eqb = 0;
+                if (!lean_verify_finish(S, vp, mpos, mcand, mlimit, n, lane, gate, mc, eqb)) { mb &= ~(1u << win); continue; }
+                wmask |= upto_win;
+                // ---- the match: remember it
+                pend.valid = true; pend.post = post; pend.from_search = from_search;
+                pend.anchor = anchor; pend.mpos = mpos; pend.mcand = mcand; pend.mc = mc; pend.eqb = eqb;
+                // post rounds: lane t >= 1 of the emission needs the byte at anchor + t - 1, held by slot s_lane + t - 1
+                pend.lit = post ? __shfl_sync(kFull, lit, (lane + s_lane - 1) & 31) : 0u;
+                const uint32_t nbase = mpos + 4u + mc;      // first position after the match
+                anchor = nbase;
+                if (nbase >= mfl1) { finished = true; break; }          // lz4.c:2227
+                const uint32_t nl = nbase - base + 1u;      // slot of nbase in this round's layout
+                if (!post || clashed || nl > 31u) { base = nbase; next_post = true; break; }
+                wmask |= 1u << (nl - 2u);                   // insert of nbase-2 (lz4.c:2230)
+                s_lane = (int)nl;
             }
 
             // ---------------- commit the table writes the serial algorithm would have made ----------------
-            // slots up to the winning match, or up to (not including) the slot that ran into the end of the block
-            const int limit = win_is_match ? win : win - 1;
-            bool wr = valid && lane <= limit;
-            if (clashed && wr) {                            // last writer per bucket
-                const unsigned upto = limit >= 31 ? kFull : ((2u << limit) - 1u);
-                const unsigned later = lane >= 31 ? 0u : (peers & upto & ~((2u << lane) - 1u));
-                if (later) wr = false;
-            }
+            bool wr = valid && ((wmask >> lane) & 1u);
+            if (clashed && wr && lane < 31 && (peers & wmask & ~((2u << lane) - 1u))) wr = false;   // last writer per bucket
             if (wr) tab[h] = cur | (chk << 19);
             __syncwarp();
-            if (win >= 32) {                                // nothing happened: next 32 probes of the same search
-                if (post) { fwd = base + 31; step = 1; nb = 64 + 30; post = false; }
-                else { fwd = __shfl_sync(kFull, cur + my_step, 31); step = (nb + 31) >> 6; nb += 32; }
-                continue;
-            }
-            if (!win_is_match) break;                       // search ran into the end of the block -> closing literals
-
-            // ---------------- the match: remember it, move on ----------------
-            pend.valid = true; pend.post = post; pend.from_search = !(post && win == 1);
-            pend.anchor = anchor; pend.mpos = mpos; pend.mcand = mcand; pend.mc = mc; pend.eqb = eqb;
-            pend.lit = lo & 0xffu;
-            base = mpos + 4 + mc;                           // first position after the match
-            anchor = base;
-            if (base >= mfl1) break;                        // lz4.c:2227
-            post = true;
+            if (next_post) post = true;
         }
         if (pend.valid && !refused && !lean_emit(pend, src, dst, op, limited, cap, lane)) refused = true;
     }
