@@ -95,3 +95,46 @@ def test_native_entry_points(oracle, corpus):
     assert L.snappy_uncompress(dst.ctypes.data, clen.value, back.ctypes.data, C.byref(ulen)) == 0
     assert ulen.value == n and back.tobytes() == data.tobytes()
     assert L.snappy_uncompress(dst[3:].ctypes.data, 5, back.ctypes.data, C.byref(ulen)) == 1   # SNAPPY_INVALID_INPUT
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_pipelined_host_transfers(gpu_lib, oracle, codec):
+    """Large PINNED host buffers take the pipelined paths of aocl_llc_compress / aocl_llc_decompress (striped
+    or in-order H2D behind the encoders' input watermark; slab-wise H2D | decode | D2H).  Same bytes as the
+    oracle, and the same bytes as the plain path (pageable buffers)."""
+    import ctypes as C
+    import torch
+    import llc_b200
+    from llc_b200 import gen
+    n = 160 << 20                                            # 640 LZ4 / Snappy partitions: more than one decode slab
+    data = np.concatenate([gen.text_like(96 << 20, seed=21), gen.mixed_entropy(32 << 20), gen.log_like(32 << 20, seed=22)])
+    assert len(data) == n
+    want = oracle.compress(data, codec)
+    L = llc_b200.load()
+    cap = L.aocl_gpu_compress_bound(codec, n)
+    h_in = torch.from_numpy(data).pin_memory()
+    h_comp = torch.zeros(cap, dtype=torch.uint8).pin_memory()
+    h_back = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    d = llc_b200.AoclDesc()
+    d.optOff, d.optLevel, d.measureStats = 0, -1, 0
+    assert L.aocl_llc_setup(C.byref(d), codec) == 0
+    for _ in range(2):                                       # twice: the staging buffers and the watermark are reused
+        d.inBuf, d.inSize, d.outBuf, d.outSize = h_in.data_ptr(), n, h_comp.data_ptr(), cap
+        r = L.aocl_llc_compress(C.byref(d), codec)
+        assert r == len(want)
+        assert h_comp[:r].numpy().tobytes() == want
+        h_back.zero_()
+        d.inBuf, d.inSize, d.outBuf, d.outSize = h_comp.data_ptr(), r, h_back.data_ptr(), n
+        assert L.aocl_llc_decompress(C.byref(d), codec) == n
+        assert h_back.numpy().tobytes() == data.tobytes()
+    # a damaged partition in the middle of the stream is reported by the pipelined path as well
+    bad = h_comp.clone().pin_memory()
+    mid = len(want) // 2
+    bad[mid: mid + 64] = 0xFF
+    h_back.zero_()
+    d.inBuf, d.inSize, d.outBuf, d.outSize = bad.data_ptr(), len(want), h_back.data_ptr(), n
+    r = L.aocl_llc_decompress(C.byref(d), codec)
+    assert r < 0 or h_back.numpy().tobytes() != data.tobytes()
+    # pageable buffers (plain path) give the same stream
+    r2, got = gpu_lib.compress(data, codec, cap=cap)
+    assert r2 == len(want) and got == want
