@@ -387,7 +387,7 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
         // same placement rule as the LZ4 encoder: fragments are serial chains, the 32 KiB table caps
         // the shared-memory flavour at 7 warps per SM, the global-table flavour runs snappy_gtab per SM
         int sn_gtab = c->snappy_gtab_ctas_per_sm;
-        if (sn_gtab < 0) sn_gtab = F > (uint32_t)c->sm_count * 7u ? 16 : 0;   // measured: 0 -> 74 ms, 16 -> 60 ms, 32 -> 78 ms (L2 thrash)
+        if (sn_gtab < 0) sn_gtab = F > (uint32_t)c->sm_count * 6u ? 16 : 0;   // measured: 0 -> 74 ms, 16 -> 60 ms, 32 -> 78 ms (L2 thrash)
         const uint32_t g_grid = (uint32_t)sn_gtab * (uint32_t)c->sm_count < F ? (uint32_t)sn_gtab * (uint32_t)c->sm_count : F;
         const size_t o_len = 0, o_off = align_up(o_len + sizeof(uint32_t) * (F + 2), 256);
         const size_t o_tab = align_up(o_off + sizeof(uint64_t) * (F + 1), 256);
@@ -411,7 +411,7 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
             cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
         }
         if (F && g_grid) LLC_LAUNCH(snappy_encode_frags_gtab_kernel, g_grid, 32, 0, c->stream, src, g, scratch, slot, frag_len, ticket, tables, in_flag, c->d_res);
-        else if (F) LLC_LAUNCH(snappy_encode_frags_kernel, (F < (uint32_t)c->sm_count * 7u ? F : (uint32_t)c->sm_count * 7u), 32, 32768,
+        else if (F) LLC_LAUNCH(snappy_encode_frags_kernel, (F < (uint32_t)c->sm_count * 6u ? F : (uint32_t)c->sm_count * 6u), 32, 32768,
                                c->stream, src, g, scratch, slot, frag_len, ticket, in_flag, c->d_res);
         if (F && g_grid && c->l2_persist_bytes) {              // later kernels on this stream: no window
             cudaStreamAttrValue av = {};
