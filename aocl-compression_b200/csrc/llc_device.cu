@@ -387,7 +387,7 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
         // same placement rule as the LZ4 encoder: fragments are serial chains, the 32 KiB table caps
         // the shared-memory flavour at 7 warps per SM, the global-table flavour runs snappy_gtab per SM
         int sn_gtab = c->snappy_gtab_ctas_per_sm;
-        if (sn_gtab < 0) sn_gtab = F > (uint32_t)c->sm_count * 6u ? 16 : 0;   // measured: 0 -> 74 ms, 16 -> 60 ms, 32 -> 78 ms (L2 thrash)
+        if (sn_gtab < 0) sn_gtab = F > (uint32_t)c->sm_count * 6u ? 24 : 0;   // measured (lean encoder): 12 -> 40.3 ms, 16 -> 32.8, 20 -> 31.3, 24 -> 29.2, 28 -> 45.6 (tables outgrow L2)
         const uint32_t g_grid = (uint32_t)sn_gtab * (uint32_t)c->sm_count < F ? (uint32_t)sn_gtab * (uint32_t)c->sm_count : F;
         const size_t o_len = 0, o_off = align_up(o_len + sizeof(uint32_t) * (F + 2), 256);
         const size_t o_tab = align_up(o_off + sizeof(uint64_t) * (F + 1), 256);

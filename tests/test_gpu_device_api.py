@@ -43,11 +43,13 @@ def test_device_resident_round_trip(torch_mod, ctx, oracle, corpus, codec):
     d_in = dev(torch, data)
     cap = ctx.L.aocl_gpu_compress_bound(codec, len(data))
     d_comp = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()                                 # torch fills on its stream, the library runs on its own
     csz = ctx.compress(codec, d_in, d_comp)
     want = oracle.compress(data, codec)
     assert csz == len(want)
     assert d_comp[:csz].cpu().numpy().tobytes() == want
     d_back = torch.zeros(len(data), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     assert ctx.decompress(codec, d_comp, csz, d_back) == len(data)
     assert torch.equal(d_back, d_in)
     # host API with device pointers: no staging, same bytes
@@ -55,6 +57,7 @@ def test_device_resident_round_trip(torch_mod, ctx, oracle, corpus, codec):
     desc = llc_b200.AoclDesc()
     assert ctx.L.aocl_llc_setup(C.byref(desc), codec) == 0
     d_comp2 = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     desc.inBuf, desc.inSize, desc.outBuf, desc.outSize = d_in.data_ptr(), len(data), d_comp2.data_ptr(), cap
     assert ctx.L.aocl_llc_compress(C.byref(desc), codec) == csz
     assert torch.equal(d_comp2[:csz], d_comp[:csz])
@@ -78,6 +81,7 @@ def test_partition_range_decode(torch_mod, ctx, oracle, corpus, codec):
         lo, hi = shard.partition_range(T, r, world)
         nbytes = int(sum(int(entries[i, 2]) for i in range(lo, hi) if entries[i, 1] > 0))
         d_out = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
         ctx.decompress_range_async(codec, d_stream, len(stream), d_out, lo, hi - lo, int(origins[lo]))
         assert ctx.finish() == nbytes
         pieces.append(d_out[:nbytes].cpu().numpy())
@@ -101,6 +105,7 @@ def test_batched_pages(torch_mod, ctx, oracle, codec):
     in_sizes = torch.tensor(sizes, dtype=torch.int32, device="cuda")
     out_caps = torch.full((24,), bound, dtype=torch.int32, device="cuda")
     status = torch.zeros(24, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     ctx.compress_batch_async(codec, in_ptrs, in_sizes, out_ptrs, out_caps, status, 24)
     assert ctx.finish() == 0
     st = status.cpu().numpy()
@@ -114,6 +119,7 @@ def test_batched_pages(torch_mod, ctx, oracle, codec):
     csizes = torch.tensor([len(w) for w in want], dtype=torch.int32, device="cuda")
     caps = torch.tensor([max(s, 0) for s in sizes], dtype=torch.int32, device="cuda")
     status2 = torch.zeros(24, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     ctx.decompress_batch_async(codec, out_ptrs, csizes, back_ptrs, caps, status2, 24)
     assert ctx.finish() == 0
     st2 = status2.cpu().numpy()
@@ -125,6 +131,7 @@ def test_batched_pages(torch_mod, ctx, oracle, codec):
     bad = d_out.clone()
     bad[bound * 3 + 100: bound * 3 + 116] = 0xFF
     bad_ptrs = torch.tensor([bad.data_ptr() + bound * i for i in range(24)], dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     ctx.decompress_batch_async(codec, bad_ptrs, csizes, back_ptrs, caps, status2, 24)
     failed = -ctx.finish()
     st3 = status2.cpu().numpy()
