@@ -38,7 +38,8 @@ constexpr uint32_t kTChunkLog = 12, kTChunk = 1u << kTChunkLog;
 constexpr uint32_t kTMargin = 384;                       // a regular sequence reads < 280 bytes past its token
 constexpr uint32_t kTBuf = kTChunk + kTMargin;           // multiple of 16
 constexpr uint32_t kTSpan = 16384;                       // output bytes per group (truncated beyond)
-constexpr uint32_t kTSpanBlocks = kTSpan / 32 + 32;
+constexpr uint32_t kTBlkLog = 4;                         // block map granularity: 16 output bytes
+constexpr uint32_t kTSpanBlocks = (kTSpan >> kTBlkLog) + 32;
 constexpr uint32_t kTFastTail = 300;                     // tokens this close to the stream end take the slow step
 constexpr uint32_t kTPiece = 16384;                      // slow-step copy granule
 constexpr uint32_t kTNone = 0xffffu;
@@ -54,7 +55,7 @@ struct TileShared {
     uint16_t dl[MAXSEQ + 32];                            // output position of each sequence relative to the group (+ end)
     uint16_t seq_start[MAXSEQ];
     uint16_t llen[MAXSEQ];                               // literal length; bit 15: its match part cannot be redirected into
-    uint16_t blk2seq[kTSpanBlocks];                      // sequence covering byte 32*B of the group span
+    uint16_t blk2seq[kTSpanBlocks];                      // sequence covering byte (B << kTBlkLog) of the group span
     uint32_t done_bits[MAXSEQ / 32 + 1];
     uint32_t batch_tot[MAXSEQ / 32 + 1];
     uint16_t anchors[MAXSEQ / 64 + 2];                   // 64-sequence anchors
@@ -107,6 +108,20 @@ __device__ __forceinline__ void lds_unaligned8(const uint32_t* w32, uint32_t idx
 }
 // the low min(n, 8) bytes of (lo, hi) to ring positions pos, pos+1, ...
 __device__ __forceinline__ void sts_bytes8(uint8_t* ring, uint32_t pos, uint32_t lo, uint32_t hi, uint32_t n) {
+    const uint32_t p = pos & 65535u;
+    if (p <= 65536u - 8u) {                                 // no wrap inside these 8 bytes: one address, immediate offsets
+        uint8_t* q = ring + p;
+        const unsigned m = n >= 8u ? 0xffu : ((1u << n) - 1u);
+        if (m & 1u) q[0] = (uint8_t)lo;
+        if (m & 2u) q[1] = (uint8_t)(lo >> 8);
+        if (m & 4u) q[2] = (uint8_t)(lo >> 16);
+        if (m & 8u) q[3] = (uint8_t)(lo >> 24);
+        if (m & 16u) q[4] = (uint8_t)hi;
+        if (m & 32u) q[5] = (uint8_t)(hi >> 8);
+        if (m & 64u) q[6] = (uint8_t)(hi >> 16);
+        if (m & 128u) q[7] = (uint8_t)(hi >> 24);
+        return;
+    }
 #pragma unroll
     for (uint32_t j = 0; j < 8; j++)
         if (j < n) ring[(pos + j) & 65535u] = (uint8_t)((j < 4 ? lo : hi) >> (8u * (j & 3u)));
@@ -138,7 +153,7 @@ struct TileLz4 {
 };
 
 struct TileSnappy {
-    static constexpr int kMaxSeq = 1408;                 // elements per group (a 4 KiB chunk of text holds ~1200)
+    static constexpr int kMaxSeq = 1376;                 // elements per group (a 4 KiB chunk of text holds ~1200); sized to keep 2 CTAs per SM
     static constexpr bool kHasLit = false;               // an element is either literals or a copy
     static constexpr uint32_t kEndSlack = 0;
 
@@ -500,7 +515,7 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
             if (k == nseq - 1) sh.dl[nseq] = (uint16_t)(end - op0);
             const bool bad = (ml != 0 && (off == 0 || off > dm - st.a)) || end > lim_o;
             if (bad) atomicMin(&sh.first_bad, k);
-            for (uint32_t B = (dlk - op0 + 31u) >> 5; (B << 5) < end - op0 && B < kTSpanBlocks; B++) sh.blk2seq[B] = (uint16_t)k;
+            for (uint32_t B = (dlk - op0 + (1u << kTBlkLog) - 1u) >> kTBlkLog; (B << kTBlkLog) < end - op0 && B < kTSpanBlocks; B++) sh.blk2seq[B] = (uint16_t)k;
         }
         if (!Fmt::kHasLit) {                                         // pure-literal elements never have to be waited for
             const unsigned z = __ballot_sync(kFull, k < nseq && (f_len[r] >> 16) == 0);
@@ -558,7 +573,7 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
             bool moved = false;
             if (act && sp >= op0) {
                 const uint32_t x = sp - op0;
-                uint32_t j = sh.blk2seq[x >> 5];
+                uint32_t j = sh.blk2seq[x >> kTBlkLog];
                 while (j < k && sh.dl[j + 1] <= x) j++;
                 const uint32_t lj = sh.llen[j];
                 const uint32_t dmj = (uint32_t)sh.dl[j] + (lj & 0x7fffu);
@@ -592,7 +607,7 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
             const uint32_t e = min(s + ml, dm);                      // source bytes that precede the destination
             if (e > op0) {
                 const uint32_t x = max(s, op0) - op0, y = e - 1u - op0;
-                uint32_t j = sh.blk2seq[x >> 5];
+                uint32_t j = sh.blk2seq[x >> kTBlkLog];
 #ifdef LLC_TILE_PROF
                 if (j > k || sh.dl[j] > x) TWATCH(2);
 #endif
