@@ -138,3 +138,31 @@ def test_pipelined_host_transfers(gpu_lib, oracle, codec):
     # pageable buffers (plain path) give the same stream
     r2, got = gpu_lib.compress(data, codec, cap=cap)
     assert r2 == len(want) and got == want
+
+
+def test_concurrent_host_threads(gpu_lib, oracle, corpus):
+    """SURVEY 8(b) threading: calls from several host threads on distinct descriptors must be safe
+    (the reference has no locks on the data path; the GPU library serialises on its context)."""
+    import threading
+    jobs = [(ol.LZ4, corpus["text"][:900001]), (ol.SNAPPY, corpus["log"][:700003]),
+            (ol.LZ4, corpus["mixed"][:1200007]), (ol.SNAPPY, corpus["text"][:500009])]
+    want = [oracle.compress(d, c) for c, d in jobs]
+    errors = []
+
+    def work(k):
+        codec, data = jobs[k]
+        try:
+            for _ in range(3):
+                r, got = gpu_lib.compress(data, codec)
+                assert r == len(want[k]) and got == want[k], ("compress", k)
+                r2, back = gpu_lib.decompress(got, codec, len(data))
+                assert r2 == len(data) and back == data.tobytes(), ("decompress", k)
+        except Exception as e:                               # noqa: BLE001 - collected and re-raised below
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
