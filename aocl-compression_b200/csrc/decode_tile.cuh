@@ -20,7 +20,7 @@
 //   * the finished span is flushed ring -> HBM with aligned 16-byte stores, so HBM only sees
 //     coalesced traffic: C bytes in through TMA, U bytes out through STG.128.
 //
-// Anything irregular -- length runs >= 270 (a 255 extension byte), the last ~300 bytes of a stream,
+// Anything irregular -- length runs >= 270 (a 255 extension byte), the closing sequences of a stream,
 // sequences that would cross the output capacity, malformed input -- is executed one sequence at a
 // time by the fully checked slow step, which mirrors lz4_slow_sequence()/snappy_decode_warp() and
 // through them the reference decoders (algos/lz4/lz4.c:3806-4305; algos/snappy/snappy.cc:1466-1570,
@@ -40,7 +40,6 @@ constexpr uint32_t kTBuf = kTChunk + kTMargin;           // multiple of 16
 constexpr uint32_t kTSpan = 16384;                       // output bytes per group (truncated beyond)
 constexpr uint32_t kTBlkLog = 4;                         // block map granularity: 16 output bytes
 constexpr uint32_t kTSpanBlocks = (kTSpan >> kTBlkLog) + 32;
-constexpr uint32_t kTFastTail = 300;                     // tokens this close to the stream end take the slow step
 constexpr uint32_t kTPiece = 16384;                      // slow-step copy granule
 constexpr uint32_t kTNone = 0xffffu;
 constexpr uint32_t kTCapMax = 0xffffff00u;
@@ -150,6 +149,11 @@ struct TileLz4 {
         s.nxt = special ? kTNone : q + 2u + (extM ? 1u : 0u);
         return s;
     }
+    // A sequence is regular only if it is not one of the closing ones: its literals end at least 8 bytes
+    // before the end of the stream (lz4.c:4104-4164), which also keeps its offset / length bytes inside.
+    __device__ static __forceinline__ bool ends_inside(const TSeq& s, uint32_t cbase, uint32_t iend) {
+        return cbase + s.lit + s.ll + 8u <= iend;
+    }
 };
 
 struct TileSnappy {
@@ -173,6 +177,10 @@ struct TileSnappy {
             s.ml = 1u + (tag >> 2); s.off = b1 | (b2 << 8); s.nxt = i + 3u;
         }
         return s;
+    }
+    // an element is regular only if all of it lies inside the stream
+    __device__ static __forceinline__ bool ends_inside(const TSeq& s, uint32_t cbase, uint32_t iend) {
+        return cbase + s.nxt <= iend;
     }
 };
 
@@ -400,7 +408,8 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
 #pragma unroll
         for (int j = 0; j < kPer; j++) {
             const uint32_t i = tid + j * kTThreads;
-            v[j] = (cbase + i < fast_i_ex) ? Fmt::parse(bp, i).nxt : kTNone;
+            const TSeq sq = Fmt::parse(bp, i);               // may read stale bytes past the end of the stream: discarded below
+            v[j] = (cbase + i < fast_i_ex && sq.nxt != kTNone && Fmt::ends_inside(sq, cbase, fast_i_ex)) ? sq.nxt : kTNone;
         }
 #pragma unroll
         for (int j = 0; j < kPer; j++) sh.n1[tid + j * kTThreads] = (uint16_t)v[j];
@@ -703,7 +712,9 @@ __device__ __forceinline__ int64_t tile_decode_unit(TileShared<Fmt>& sh, uint32_
     st.ip = pad; st.op = st.a; st.flushed = st.a;
     st.par = par; st.pend = 0; st.bufc[0] = st.bufc[1] = -1; st.tabc = -1;
     st.last = last;
-    const uint32_t fast_i_ex = st.iend > kTFastTail + pad ? st.iend - kTFastTail : 0u;
+    // Tokens take the fast path up to the end of the stream; the parse itself keeps the closing sequences
+    // (and anything that would read past the end) for the checked step (Fmt::ends_inside).
+    const uint32_t fast_i_ex = st.iend;
     int status = 0;
     while (status == 0) {
         int slow = 1;
