@@ -1,5 +1,6 @@
 // decode_tile.cuh -- tile decoder: one 512-thread CTA per unit (RAP partition or page), LANE PER
-// SEQUENCE, with the last 64 KiB of output kept in a shared-memory ring.
+// SEQUENCE for the parse and THREAD PER BYTE for the copies, with the last 32 KiB of output kept in a
+// shared-memory ring.
 //
 // Why.  A unit is one serial token chain, and the warp-per-unit decoders (lz4_decode_ring.cuh) spend
 // ~160 warp instructions per 10-byte sequence: the whole GPU ends up issue bound at ~1 % of the HBM
@@ -14,9 +15,18 @@
 //     and 8-hop/1-hop links expand the anchors into the list of real sequence starts;
 //   * a block scan of the sequence lengths gives every sequence its output position; offsets and
 //     capacity are validated there (the first irregular sequence truncates the group);
-//   * COPY is lane per sequence inside shared memory: literals chunk -> ring, matches ring -> ring
-//     in dependency rounds (a match waits for the sequences its source overlaps, tracked in a
-//     bitmap; sources older than the group are always final);
+//   * COPY is THREAD PER OUTPUT BYTE.  Byte x of the group finds its sequence (a bitmap of sequence
+//     starts + the sequence that covers the first byte of every 32-byte row), and then either takes
+//     its literal from the chunk buffer, or its match source from the ring (sources older than the
+//     group are final; sources that have left the 32 KiB ring are read back from HBM/L2), or -- a
+//     match whose source lies inside the group -- records a POINTER to that byte.  Text-like data
+//     chains every occurrence of a string to the previous one, so these pointers form chains hundreds
+//     of links deep: they are resolved by pointer jumping, P[x] = P[P[x]], until every chain has
+//     reached a byte that is known.  A table entry holds either a pointer (< 16384) or 0xFF00 | value,
+//     so one 16-bit load tells a reader both whether the byte is known and what it is; concurrent
+//     updates are benign (any entry read is an ancestor of x with the same final value).  A first
+//     version copied lane-per-sequence in dependency rounds with source forwarding: 62.5 % of the
+//     group time (profiles/r1_v10_*), most of it spent polling for producers;
 //   * the finished span is flushed ring -> HBM with aligned 16-byte stores, so HBM only sees
 //     coalesced traffic: C bytes in through TMA, U bytes out through STG.128.
 //
@@ -33,29 +43,31 @@ namespace llc {
 
 constexpr int kTThreads = 512;
 constexpr int kTWarps = kTThreads / 32;
-constexpr uint32_t kTRingMask = 65535u;
+constexpr uint32_t kTRing = 32768u, kTRingMask = kTRing - 1u;
 constexpr uint32_t kTChunkLog = 12, kTChunk = 1u << kTChunkLog;
 constexpr uint32_t kTMargin = 384;                       // a regular sequence reads < 280 bytes past its token
 constexpr uint32_t kTBuf = kTChunk + kTMargin;           // multiple of 16
 constexpr uint32_t kTSpan = 16384;                       // output bytes per group (truncated beyond)
-constexpr uint32_t kTBlkLog = 4;                         // block map granularity: 16 output bytes
-constexpr uint32_t kTSpanBlocks = (kTSpan >> kTBlkLog) + 32;
-constexpr uint32_t kTPiece = 16384;                      // slow-step copy granule
+constexpr uint32_t kTRows = kTSpan / 32;                 // 32-byte rows of a group span: one warp handles one row at a time
+constexpr uint32_t kTKnown = 0xFF00u;                    // P entry >= kTKnown: the byte is known, value in the low 8 bits
+constexpr uint32_t kTPiece = 16384;                      // slow-step copy granule (<= half the ring)
+static_assert(kTRows == (uint32_t)kTThreads && kTSpan < kTKnown && kTSpan + kTPiece <= kTRing, "tile geometry");
 constexpr uint32_t kTNone = 0xffffu;
 constexpr uint32_t kTCapMax = 0xffffff00u;
 
 template <class Fmt>
 struct TileShared {
     static constexpr int MAXSEQ = Fmt::kMaxSeq;
-    alignas(128) uint8_t ring[65536];
+    alignas(128) uint8_t ring[kTRing];
     alignas(128) uint8_t inbuf[2][kTBuf];
     uint16_t n1[kTChunk], ta[kTChunk], tb[kTChunk];
-    uint32_t src[MAXSEQ];                                // current source position of each match (redirected)
+    uint16_t P[kTSpan];                                  // per output byte of the group: pointer to its source byte, or kTKnown | value
+    uint32_t src[MAXSEQ];                                // match offset | chunk index of the literals << 16
     uint16_t dl[MAXSEQ + 32];                            // output position of each sequence relative to the group (+ end)
     uint16_t seq_start[MAXSEQ];
-    uint16_t llen[MAXSEQ];                               // literal length; bit 15: its match part cannot be redirected into
-    uint16_t blk2seq[kTSpanBlocks];                      // sequence covering byte (B << kTBlkLog) of the group span
-    uint32_t done_bits[MAXSEQ / 32 + 1];
+    uint16_t llen[MAXSEQ];                               // literal length
+    uint32_t startbits[kTRows + 1];                      // bit x: a sequence starts at byte x of the group span
+    uint16_t row2seq[kTRows + 32];                       // sequence covering the first byte of every 32-byte row
     uint32_t batch_tot[MAXSEQ / 32 + 1];
     uint16_t anchors[MAXSEQ / 64 + 2];                   // 64-sequence anchors
     uint16_t anchors8[8];                                // then up to seven 8-sequence anchors
@@ -98,34 +110,6 @@ __device__ unsigned long long g_tile_prof[32];
 #define TWATCH(code) do { atomicAdd(&g_tile_prof[24 + (code)], 1ull); } while (0)
 constexpr uint32_t kTSpinMax = 1u << 22;
 
-// 8 bytes starting at byte index idx of a 4-byte aligned shared array (word index wrapped with wmask)
-__device__ __forceinline__ void lds_unaligned8(const uint32_t* w32, uint32_t idx, uint32_t wmask, uint32_t& lo, uint32_t& hi) {
-    const uint32_t wi = idx >> 2, sh = (idx & 3u) * 8u;
-    const uint32_t w0 = w32[wi & wmask], w1 = w32[(wi + 1u) & wmask], w2 = w32[(wi + 2u) & wmask];
-    lo = __funnelshift_r(w0, w1, sh);
-    hi = __funnelshift_r(w1, w2, sh);
-}
-// the low min(n, 8) bytes of (lo, hi) to ring positions pos, pos+1, ...
-__device__ __forceinline__ void sts_bytes8(uint8_t* ring, uint32_t pos, uint32_t lo, uint32_t hi, uint32_t n) {
-    const uint32_t p = pos & 65535u;
-    if (p <= 65536u - 8u) {                                 // no wrap inside these 8 bytes: one address, immediate offsets
-        uint8_t* q = ring + p;
-        const unsigned m = n >= 8u ? 0xffu : ((1u << n) - 1u);
-        if (m & 1u) q[0] = (uint8_t)lo;
-        if (m & 2u) q[1] = (uint8_t)(lo >> 8);
-        if (m & 4u) q[2] = (uint8_t)(lo >> 16);
-        if (m & 8u) q[3] = (uint8_t)(lo >> 24);
-        if (m & 16u) q[4] = (uint8_t)hi;
-        if (m & 32u) q[5] = (uint8_t)(hi >> 8);
-        if (m & 64u) q[6] = (uint8_t)(hi >> 16);
-        if (m & 128u) q[7] = (uint8_t)(hi >> 24);
-        return;
-    }
-#pragma unroll
-    for (uint32_t j = 0; j < 8; j++)
-        if (j < n) ring[(pos + j) & 65535u] = (uint8_t)((j < 4 ? lo : hi) >> (8u * (j & 3u)));
-}
-
 // ------------------------------------------------------------------------------------------------
 // Formats
 // ------------------------------------------------------------------------------------------------
@@ -157,7 +141,7 @@ struct TileLz4 {
 };
 
 struct TileSnappy {
-    static constexpr int kMaxSeq = 1376;                 // elements per group (a 4 KiB chunk of text holds ~1200); sized to keep 2 CTAs per SM
+    static constexpr int kMaxSeq = 1280;                 // elements per group (a 4 KiB chunk of text holds ~1200); sized to keep 2 CTAs per SM
     static constexpr bool kHasLit = false;               // an element is either literals or a copy
     static constexpr uint32_t kEndSlack = 0;
 
@@ -238,7 +222,7 @@ __device__ __forceinline__ void tile_slow_match(TileShared<Fmt>& sh, TileState& 
         const uint32_t n = min(kTPiece, ml - done);
         const uint32_t d = st.op + done;
         const uint32_t hi = d + n;
-        const uint32_t ring_lo = hi > 65536u ? hi - 65536u : 0u;      // older bytes have left the ring (they are flushed)
+        const uint32_t ring_lo = hi > kTRing ? hi - kTRing : 0u;      // older bytes have left the ring (they are flushed)
         for (uint32_t j = threadIdx.x; j < n; j += kTThreads) {
             const uint32_t k = done + j;
             const uint32_t sp = s + (periodic ? k % off : k);
@@ -458,7 +442,7 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
         sh.nanch = na; sh.nanch8 = na8; sh.ntail = nt; sh.end_kind = kind; sh.end_pos = p;
         sh.first_bad = 0xffffffffu;
     }
-    if (tid < MAXSEQ / 32 + 1) sh.done_bits[tid] = 0;
+    sh.startbits[tid] = 0;                                           // kTRows == kTThreads
     __syncthreads();
     const uint32_t nanch = sh.nanch, ntail = sh.ntail;
     const uint32_t n8a = nanch * 8u + sh.nanch8;                     // 8-sequence runs
@@ -517,18 +501,17 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
             const uint32_t ll = f_len[r] & 0xffffu, ml = f_len[r] >> 16, off = f_src[r] & 0xffffu;
             const uint32_t dlk = op0 + sh.batch_tot[bt] + f_dl[r];
             const uint32_t dm = dlk + ll, end = dm + ml;
-            f_dl[r] = dlk;
             sh.dl[k] = (uint16_t)(dlk - op0);
-            sh.llen[k] = (uint16_t)(ll | ((ml == 0 || off < ml) ? 0x8000u : 0u));
-            sh.src[k] = dm - off;
+            sh.llen[k] = (uint16_t)ll;
+            sh.src[k] = off | (f_src[r] & 0xffff0000u);              // offset | literal index
             if (k == nseq - 1) sh.dl[nseq] = (uint16_t)(end - op0);
             const bool bad = (ml != 0 && (off == 0 || off > dm - st.a)) || end > lim_o;
             if (bad) atomicMin(&sh.first_bad, k);
-            for (uint32_t B = (dlk - op0 + (1u << kTBlkLog) - 1u) >> kTBlkLog; (B << kTBlkLog) < end - op0 && B < kTSpanBlocks; B++) sh.blk2seq[B] = (uint16_t)k;
-        }
-        if (!Fmt::kHasLit) {                                         // pure-literal elements never have to be waited for
-            const unsigned z = __ballot_sync(kFull, k < nseq && (f_len[r] >> 16) == 0);
-            if (lane == 0 && z) atomicOr(&sh.done_bits[bt], z);
+            const uint32_t rel = dlk - op0, erel = end - op0;
+            if (rel < kTSpan) {                                      // sequences beyond the span are never executed
+                atomicOr(&sh.startbits[rel >> 5], 1u << (rel & 31u));
+                for (uint32_t R = (rel + 31u) >> 5; (R << 5) < erel && R < kTRows; R++) sh.row2seq[R] = (uint16_t)k;
+            }
         }
     }
     __syncthreads();
@@ -536,150 +519,51 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     const uint32_t nexec = min(nseq, sh.first_bad);
     TC(3, nexec);
     if (nexec == 0) return 1;                                        // first sequence is irregular: slow step at st.ip
-    const uint32_t g_hi = op0 + sh.dl[nexec];
-    const uint32_t ring_lo = g_hi > 65536u ? g_hi - 65536u : 0u;
+    const uint32_t G = sh.dl[nexec];                                 // bytes this group produces
+    const uint32_t g_hi = op0 + G;
+    const uint32_t ring_lo = g_hi > kTRing ? g_hi - kTRing : 0u;     // older bytes have left the ring (they are flushed)
+    const uint32_t nrows = (G + 31u) >> 5;
 
-    // ---- literals: chunk buffer -> ring, one lane per sequence (runs > 32 bytes by the whole warp)
-#pragma unroll
-    for (int r = 0; r < kRounds; r++) {
-        const uint32_t bt = warp + r * kTWarps, k = bt * 32u + lane;
-        if (bt * 32u >= nexec) break;
-        const bool act = k < nexec;
-        const uint32_t ll = act ? (f_len[r] & 0xffffu) : 0u, lit = f_src[r] >> 16, dlk = f_dl[r];
-        const uint32_t n = ll <= 32u ? ll : 0u;
-        const uint32_t mx = warp_max_u32(n);
-        for (uint32_t t = 0; t < mx; t += 8) {
-            if (t < n) {
-                uint32_t lo, hi;
-                lds_unaligned8(reinterpret_cast<const uint32_t*>(bp), lit + t, 0xffffffffu, lo, hi);
-                sts_bytes8(sh.ring, dlk + t, lo, hi, n - t);
+    // ---- every output byte finds its source.  Warp w takes rows w, w + 16, ...; lane = byte of the row.
+    //      Ring slots overwritten here held bytes older than ring_lo, which nobody reads any more.
+    uint32_t unres = 0;                                              // bit i: my byte of row warp + 16 i still follows a pointer
+    {
+        const uint32_t le_mask = (2u << lane) - 2u;                  // bits 1 .. lane
+        uint32_t i = 0;
+        for (uint32_t row = warp; row < nrows; row += kTWarps, i++) {
+            const uint32_t x = (row << 5) + lane;
+            const uint32_t k = (uint32_t)sh.row2seq[row] + (uint32_t)__popc(sh.startbits[row] & le_mask);
+            if (x < G) {
+                const uint32_t r = x - (uint32_t)sh.dl[k], ll = sh.llen[k], sv = sh.src[k];
+                const uint32_t pa = op0 + x - (sv & 0xffffu);        // match source (validated: >= st.a)
+                const bool is_lit = r < ll;
+                const bool in_group = !is_lit && pa >= op0;
+                uint32_t v = 0;
+                if (is_lit) v = bp[(sv >> 16) + r];
+                else if (!in_group) v = pa >= ring_lo ? (uint32_t)sh.ring[pa & kTRingMask] : (uint32_t)__ldcg(st.gout + pa);
+                if (in_group) unres |= 1u << i;
+                else sh.ring[(op0 + x) & kTRingMask] = (uint8_t)v;
+                sh.P[x] = (uint16_t)(in_group ? pa - op0 : (kTKnown | v));
             }
-        }
-        unsigned big = __ballot_sync(kFull, ll > 32u);
-        while (big) {
-            const int l = __ffs(big) - 1;
-            big &= big - 1;
-            const uint32_t src = __shfl_sync(kFull, lit, l), d = __shfl_sync(kFull, dlk, l), len = __shfl_sync(kFull, ll, l);
-            for (uint32_t j = lane; j < len; j += 32) sh.ring[(d + j) & kTRingMask] = bp[src + j];
         }
     }
     TP(5);
 
-    // ---- source forwarding.  Text-like data chains every occurrence of a string to the previous one, so
-    //      the dependency graph of a group is hundreds of levels deep.  A match whose source lies entirely
-    //      inside the destination of an earlier match j of the group can read from j's source instead
-    //      (same bytes, older position); iterating this is pointer doubling on the chain and leaves only
-    //      the partially overlapping links as real dependencies.  Self-overlapping matches take no part.
-#pragma unroll
-    for (int r = 0; r < kRounds; r++) {
-        const uint32_t bt = warp + r * kTWarps, k = bt * 32u + lane;
-        if (bt * 32u >= nexec) break;
-        const uint32_t ll = f_len[r] & 0xffffu, ml = f_len[r] >> 16, off = f_src[r] & 0xffffu;
-        const uint32_t dm = f_dl[r] + ll;
-        uint32_t sp = dm - off;
-        bool act = k < nexec && ml != 0 && off >= ml;
-        for (int it = 0; it < 12; it++) {
-            bool moved = false;
-            if (act && sp >= op0) {
-                const uint32_t x = sp - op0;
-                uint32_t j = sh.blk2seq[x >> kTBlkLog];
-                while (j < k && sh.dl[j + 1] <= x) j++;
-                const uint32_t lj = sh.llen[j];
-                const uint32_t dmj = (uint32_t)sh.dl[j] + (lj & 0x7fffu);
-                if (j < k && !(lj & 0x8000u) && x >= dmj && x + ml <= sh.dl[j + 1]) {
-                    const uint32_t cand = ((volatile uint32_t*)sh.src)[j] + (x - dmj);
-                    if (cand >= ring_lo) { sp = cand; sh.src[k] = cand; moved = true; } else act = false;
-                } else act = false;
-            } else act = false;
-            if (!__any_sync(kFull, moved)) break;
-        }
-        f_src[r] = (f_src[r] & 0xffff0000u) | 0u;                    // offset no longer needed
-        f_dl[r] = dm;                                                // match destination
-        f_len[r] = ml | ((off < ml ? off : 0u) << 16);               // ml | period << 16
-        // keep the forwarded source in place of (off | lit)
-        f_src[r] = sp;
-    }
-    __syncthreads();                                                 // every literal of the group is in the ring
-    TP(9);
-
-    // ---- matches: ring -> ring in dependency rounds
-#pragma unroll
-    for (int r = 0; r < kRounds; r++) {
-        const uint32_t bt = warp + r * kTWarps, k = bt * 32u + lane;
-        if (bt * 32u >= nexec) break;
-        const uint32_t ml = f_len[r] & 0xffffu, period = f_len[r] >> 16;
-        const uint32_t dm = f_dl[r];
-        const uint32_t s = f_src[r];
-        bool pending = k < nexec && ml != 0;
-        int jlo = 1, jhi = 0;
-        if (pending) {
-            const uint32_t e = min(s + ml, dm);                      // source bytes that precede the destination
-            if (e > op0) {
-                const uint32_t x = max(s, op0) - op0, y = e - 1u - op0;
-                uint32_t j = sh.blk2seq[x >> kTBlkLog];
-#ifdef LLC_TILE_PROF
-                if (j > k || sh.dl[j] > x) TWATCH(2);
-#endif
-                while (j < k && sh.dl[j + 1] <= x) j++;
-                jlo = (int)j;
-                while (j < k && sh.dl[j + 1] <= y) j++;
-                if (j >= k) jhi = (int)k - 1;                        // own literals are already in place
-                else if (y < (uint32_t)sh.dl[j] + (sh.llen[j] & 0x7fffu)) jhi = (int)j - 1;   // ends inside j's literals
-                else jhi = (int)j;
-            }
-        }
-        const bool far = s < ring_lo;
-        unsigned left = __ballot_sync(kFull, pending);
-        uint32_t spins = 0;
-        while (left) {
-            bool ready = pending;
-            if (ready && jlo <= jhi) {
-                const volatile uint32_t* db = sh.done_bits;
-                for (int w = jlo >> 5; w <= (jhi >> 5); w++) {
-                    const uint32_t lo_bit = (w == (jlo >> 5)) ? (uint32_t)(jlo & 31) : 0u;
-                    const uint32_t hi_bit = (w == (jhi >> 5)) ? (uint32_t)(jhi & 31) : 31u;
-                    const uint32_t mask = (0xffffffffu >> (31u - hi_bit)) & (0xffffffffu << lo_bit);
-                    if ((db[w] & mask) != mask) ready = false;
-                }
-            }
-            const unsigned rb = __ballot_sync(kFull, ready);
-            if (rb == 0) {
-                if (++spins > kTSpinMax) { if (lane == 0) { TWATCH(1); sh.abort = 1; } break; }
-                __nanosleep(20);
-                continue;
-            }
-            TC(4, 1);
-            __threadfence_block();                                   // acquire: the bytes behind the bits just read
-            const bool lane_copy = ml <= 32u && !far && period == 0; // short, in the ring, not self-overlapping
-            const uint32_t n = (ready && lane_copy) ? ml : 0u;
-            const uint32_t mx = warp_max_u32(n);
-            for (uint32_t t = 0; t < mx; t += 8) {
-                if (t < n) {
-                    uint32_t lo, hi;
-                    lds_unaligned8(reinterpret_cast<const uint32_t*>(sh.ring), (s + t) & kTRingMask, kTRingMask >> 2, lo, hi);
-                    sts_bytes8(sh.ring, dm + t, lo, hi, n - t);
-                }
-            }
-            unsigned big = __ballot_sync(kFull, ready && !lane_copy);
-            while (big) {
-                const int l = __ffs(big) - 1;
-                big &= big - 1;
-                const uint32_t bs = __shfl_sync(kFull, s, l), bd = __shfl_sync(kFull, dm, l);
-                const uint32_t blen = __shfl_sync(kFull, ml, l), bper = __shfl_sync(kFull, period, l);
-                for (uint32_t j = lane; j < blen; j += 32) {
-                    const uint32_t sp = bs + (bper ? j % bper : j);
-                    const uint8_t v = sp < ring_lo ? st.gout[sp] : sh.ring[sp & kTRingMask];
-                    sh.ring[(bd + j) & kTRingMask] = v;
-                }
-            }
-            __threadfence_block();                                   // release
-            __syncwarp();
-            if (lane == 0) atomicOr(&sh.done_bits[bt], rb);
-            if (ready) pending = false;
-            left &= ~rb;
+    // ---- pointer jumping.  Invariant: byte x has the same final value as the byte P[x] points at, and
+    //      pointers only point backwards, so every chain ends at a known byte; each round halves the chains.
+    TC(4, 1);
+    while (__syncthreads_or(unres != 0)) {
+        TC(4, 1);
+        uint32_t m = unres;
+        while (m) {
+            const uint32_t i = (uint32_t)__ffs(m) - 1u;
+            m &= m - 1u;
+            const uint32_t x = ((warp + i * kTWarps) << 5) + lane;
+            const uint32_t q = sh.P[sh.P[x]];
+            sh.P[x] = (uint16_t)q;
+            if (q >= kTKnown) { sh.ring[(op0 + x) & kTRingMask] = (uint8_t)q; unres &= ~(1u << i); }
         }
     }
-    __syncthreads();
     TP(6);
     if (sh.abort) return -1;
 
