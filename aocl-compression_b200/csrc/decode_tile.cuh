@@ -50,8 +50,9 @@ constexpr uint32_t kTBuf = kTChunk + kTMargin;           // multiple of 16
 constexpr uint32_t kTSpan = 16384;                       // output bytes per group (truncated beyond)
 constexpr uint32_t kTRows = kTSpan / 32;                 // 32-byte rows of a group span: one warp handles one row at a time
 constexpr uint32_t kTKnown = 0xFF00u;                    // P entry >= kTKnown: the byte is known, value in the low 8 bits
+constexpr uint32_t kTPtr = 0x4000u;                      // P entry in [kTPtr, 2 kTPtr): pointer to span index (entry - kTPtr)
 constexpr uint32_t kTPiece = 16384;                      // slow-step copy granule (<= half the ring)
-static_assert(kTRows == (uint32_t)kTThreads && kTSpan < kTKnown && kTSpan + kTPiece <= kTRing, "tile geometry");
+static_assert(kTRows == (uint32_t)kTThreads && kTSpan <= kTPtr && 2 * kTPtr <= kTKnown && kTSpan + kTPiece <= kTRing, "tile geometry");
 constexpr uint32_t kTNone = 0xffffu;
 constexpr uint32_t kTCapMax = 0xffffff00u;
 
@@ -61,19 +62,19 @@ struct TileShared {
     alignas(128) uint8_t ring[kTRing];
     alignas(128) uint8_t inbuf[2][kTBuf];
     uint16_t n1[kTChunk], ta[kTChunk], tb[kTChunk];
-    uint16_t P[kTSpan];                                  // per output byte of the group: pointer to its source byte, or kTKnown | value
-    uint32_t src[MAXSEQ];                                // match offset | chunk index of the literals << 16
-    uint16_t dl[MAXSEQ + 32];                            // output position of each sequence relative to the group (+ end)
+    alignas(16) uint16_t P[kTSpan];                      // per byte of the group span: 0 = not written yet, kTPtr | index of its
+                                                         // source byte, or kTKnown | value
+    uint2 sq[MAXSEQ];                                    // x: span index of the sequence | literal length << 16;
+                                                         // y: match offset | chunk index of the literals << 16
     uint16_t seq_start[MAXSEQ];
-    uint16_t llen[MAXSEQ];                               // literal length
     uint32_t startbits[kTRows + 1];                      // bit x: a sequence starts at byte x of the group span
-    uint16_t row2seq[kTRows + 32];                       // sequence covering the first byte of every 32-byte row
+    uint16_t row2seq[kTRows + 32];                       // 1 + the sequence covering the first byte of every 32-byte row (0: none)
     uint32_t batch_tot[MAXSEQ / 32 + 1];
     uint16_t anchors[MAXSEQ / 64 + 2];                   // 64-sequence anchors
     uint16_t anchors8[8];                                // then up to seven 8-sequence anchors
     uint16_t tail[8];                                    // then up to seven single sequences
     alignas(8) uint64_t bar[2];
-    uint32_t nanch, nanch8, ntail, end_kind, end_pos, first_bad, unit, abort;
+    uint32_t nanch, nanch8, ntail, end_kind, end_pos, first_bad, unit, abort, span_end;
 };
 
 struct TSeq { uint32_t nxt, lit, ll, ml, off; };         // chunk-relative indices; nxt == kTNone: irregular
@@ -90,6 +91,7 @@ struct TileState {
     uint32_t pend;           // bit b: a load into buffer b is in flight
     int32_t bufc[2];         // chunk held by / in flight into each buffer
     int32_t tabc;            // chunk the link tables describe
+    uint32_t pused;          // P entries the previous group wrote (cleared before the next one)
     bool last;
 };
 
@@ -443,6 +445,9 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
         sh.first_bad = 0xffffffffu;
     }
     sh.startbits[tid] = 0;                                           // kTRows == kTThreads
+    if (tid == 0) sh.row2seq[0] = 0;
+    for (uint32_t j = tid * 8u; j < st.pused; j += kTThreads * 8u) *reinterpret_cast<uint4*>(&sh.P[j]) = make_uint4(0, 0, 0, 0);
+    st.pused = 0;
     __syncthreads();
     const uint32_t nanch = sh.nanch, ntail = sh.ntail;
     const uint32_t n8a = nanch * 8u + sh.nanch8;                     // 8-sequence runs
@@ -492,8 +497,10 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
         if (lane + 32u < nbatch) sh.batch_tot[lane + 32] = s1 - v1;
     }
     __syncthreads();
-    const uint32_t op0 = st.op;
-    const uint32_t lim_o = st.cap >= op0 + Fmt::kEndSlack ? min(st.cap - Fmt::kEndSlack, op0 + kTSpan) : 0u;
+    // Span indices are relative to `base`, the 16-byte unit that holds the first byte of the group, so that
+    // aligned units of the span are aligned units of the ring and of the output.
+    const uint32_t op0 = st.op, base = op0 & ~15u, a0 = op0 - base;
+    const uint32_t lim_o = st.cap >= op0 + Fmt::kEndSlack ? min(st.cap - Fmt::kEndSlack, base + kTSpan) : 0u;
 #pragma unroll
     for (int r = 0; r < kRounds; r++) {
         const uint32_t bt = warp + r * kTWarps, k = bt * 32u + lane;
@@ -501,16 +508,14 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
             const uint32_t ll = f_len[r] & 0xffffu, ml = f_len[r] >> 16, off = f_src[r] & 0xffffu;
             const uint32_t dlk = op0 + sh.batch_tot[bt] + f_dl[r];
             const uint32_t dm = dlk + ll, end = dm + ml;
-            sh.dl[k] = (uint16_t)(dlk - op0);
-            sh.llen[k] = (uint16_t)ll;
-            sh.src[k] = off | (f_src[r] & 0xffff0000u);              // offset | literal index
-            if (k == nseq - 1) sh.dl[nseq] = (uint16_t)(end - op0);
+            const uint32_t rel = dlk - base, erel = end - base;
+            sh.sq[k] = make_uint2((rel & 0xffffu) | (ll << 16), f_src[r]);
+            if (k == nseq - 1) sh.span_end = erel;
             const bool bad = (ml != 0 && (off == 0 || off > dm - st.a)) || end > lim_o;
             if (bad) atomicMin(&sh.first_bad, k);
-            const uint32_t rel = dlk - op0, erel = end - op0;
             if (rel < kTSpan) {                                      // sequences beyond the span are never executed
                 atomicOr(&sh.startbits[rel >> 5], 1u << (rel & 31u));
-                for (uint32_t R = (rel + 31u) >> 5; (R << 5) < erel && R < kTRows; R++) sh.row2seq[R] = (uint16_t)k;
+                for (uint32_t R = (rel + 31u) >> 5; (R << 5) < erel && R < kTRows; R++) sh.row2seq[R] = (uint16_t)(k + 1u);
             }
         }
     }
@@ -519,31 +524,37 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     const uint32_t nexec = min(nseq, sh.first_bad);
     TC(3, nexec);
     if (nexec == 0) return 1;                                        // first sequence is irregular: slow step at st.ip
-    const uint32_t G = sh.dl[nexec];                                 // bytes this group produces
-    const uint32_t g_hi = op0 + G;
+    const uint32_t gend = nexec < nseq ? (sh.sq[nexec].x & 0xffffu) : sh.span_end;   // span index one past the group's last byte
+    const uint32_t g_hi = base + gend;
     const uint32_t ring_lo = g_hi > kTRing ? g_hi - kTRing : 0u;     // older bytes have left the ring (they are flushed)
-    const uint32_t nrows = (G + 31u) >> 5;
+    const uint32_t nrows = (gend + 31u) >> 5;
+    st.pused = (gend + 7u) & ~7u;
 
     // ---- every output byte finds its source.  Warp w takes rows w, w + 16, ...; lane = byte of the row.
-    //      Ring slots overwritten here held bytes older than ring_lo, which nobody reads any more.
+    //      The ring is only read here (sources older than the group); the group's own bytes collect in P and
+    //      move to the ring in one piece afterwards.  A source inside the group is looked at right away: the
+    //      warps walk the span front to back, so most earlier rows have been written, and whatever their
+    //      entry holds by now -- a value or a pointer further back -- is as good as the source itself.
     uint32_t unres = 0;                                              // bit i: my byte of row warp + 16 i still follows a pointer
     {
         const uint32_t le_mask = (2u << lane) - 2u;                  // bits 1 .. lane
         uint32_t i = 0;
         for (uint32_t row = warp; row < nrows; row += kTWarps, i++) {
             const uint32_t x = (row << 5) + lane;
-            const uint32_t k = (uint32_t)sh.row2seq[row] + (uint32_t)__popc(sh.startbits[row] & le_mask);
-            if (x < G) {
-                const uint32_t r = x - (uint32_t)sh.dl[k], ll = sh.llen[k], sv = sh.src[k];
-                const uint32_t pa = op0 + x - (sv & 0xffffu);        // match source (validated: >= st.a)
-                const bool is_lit = r < ll;
-                const bool in_group = !is_lit && pa >= op0;
-                uint32_t v = 0;
-                if (is_lit) v = bp[(sv >> 16) + r];
-                else if (!in_group) v = pa >= ring_lo ? (uint32_t)sh.ring[pa & kTRingMask] : (uint32_t)__ldcg(st.gout + pa);
-                if (in_group) unres |= 1u << i;
-                else sh.ring[(op0 + x) & kTRingMask] = (uint8_t)v;
-                sh.P[x] = (uint16_t)(in_group ? pa - op0 : (kTKnown | v));
+            const uint32_t k = (uint32_t)sh.row2seq[row] + (uint32_t)__popc(sh.startbits[row] & le_mask) - 1u;
+            if (x >= a0 && x < gend) {
+                const uint2 q = sh.sq[k];
+                const uint32_t r = x - (q.x & 0xffffu), ll = q.x >> 16;
+                const uint32_t pa = base + x - (q.y & 0xffffu);      // match source (validated: >= st.a)
+                uint32_t e;
+                if (r < ll) e = kTKnown | bp[(q.y >> 16) + r];
+                else if (pa >= op0) {
+                    const uint32_t p = pa - base;
+                    e = sh.P[p];
+                    if (e == 0) e = kTPtr | p;
+                    if (e < kTKnown) unres |= 1u << i;
+                } else e = kTKnown | (pa >= ring_lo ? (uint32_t)sh.ring[pa & kTRingMask] : (uint32_t)__ldcg(st.gout + pa));
+                sh.P[x] = (uint16_t)e;
             }
         }
     }
@@ -558,14 +569,35 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
         while (m) {
             const uint32_t i = (uint32_t)__ffs(m) - 1u;
             m &= m - 1u;
-            const uint32_t x = ((warp + i * kTWarps) << 5) + lane;
-            const uint32_t q = sh.P[sh.P[x]];
-            sh.P[x] = (uint16_t)q;
-            if (q >= kTKnown) { sh.ring[(op0 + x) & kTRingMask] = (uint8_t)q; unres &= ~(1u << i); }
+            uint16_t* px = &sh.P[((warp + i * kTWarps) << 5) + lane];
+            const uint32_t q = sh.P[*px - kTPtr];
+            *px = (uint16_t)q;
+            if (q >= kTKnown) unres &= ~(1u << i);
         }
     }
     TP(6);
     if (sh.abort) return -1;
+
+    // ---- P -> ring: aligned 16-byte units in one piece (32 bytes of P -> 16 bytes of ring), the partial
+    //      units at both ends byte by byte
+    {
+        const uint32_t u_lo = (a0 + 15u) >> 4, u_hi = gend >> 4;      // full units [u_lo, u_hi)
+        for (uint32_t u = u_lo + tid; u < u_hi; u += kTThreads) {
+            const uint4 lo = *reinterpret_cast<const uint4*>(&sh.P[u << 4]);
+            const uint4 hi = *reinterpret_cast<const uint4*>(&sh.P[(u << 4) + 8u]);
+            uint4 o;
+            o.x = __byte_perm(lo.x, lo.y, 0x6420); o.y = __byte_perm(lo.z, lo.w, 0x6420);
+            o.z = __byte_perm(hi.x, hi.y, 0x6420); o.w = __byte_perm(hi.z, hi.w, 0x6420);
+            *reinterpret_cast<uint4*>(&sh.ring[(base + (u << 4)) & kTRingMask]) = o;
+        }
+        if (tid < 16u) {
+            const uint32_t xh = tid;                                 // head unit (unit 0 when the group starts inside it)
+            if (xh >= a0 && xh < min(gend, u_lo << 4)) sh.ring[(base + xh) & kTRingMask] = (uint8_t)sh.P[xh];
+            const uint32_t xt = (u_hi << 4) + tid;                   // tail unit
+            if (xt >= max(a0, u_lo << 4) && xt < gend) sh.ring[(base + xt) & kTRingMask] = (uint8_t)sh.P[xt];
+        }
+    }
+    __syncthreads();
 
     // ---- ring -> HBM
     tile_flush(sh, st, g_hi, false);
@@ -594,7 +626,7 @@ __device__ __forceinline__ int64_t tile_decode_unit(TileShared<Fmt>& sh, uint32_
     st.gout = out - st.a;
     st.cap = st.a + min(cap, kTCapMax);
     st.ip = pad; st.op = st.a; st.flushed = st.a;
-    st.par = par; st.pend = 0; st.bufc[0] = st.bufc[1] = -1; st.tabc = -1;
+    st.par = par; st.pend = 0; st.bufc[0] = st.bufc[1] = -1; st.tabc = -1; st.pused = kTSpan;
     st.last = last;
     // Tokens take the fast path up to the end of the stream; the parse itself keeps the closing sequences
     // (and anything that would read past the end) for the checked step (Fmt::ends_inside).
