@@ -70,11 +70,9 @@ struct TileShared {
     uint32_t startbits[kTRows + 1];                      // bit x: a sequence starts at byte x of the group span
     uint16_t row2seq[kTRows + 32];                       // 1 + the sequence covering the first byte of every 32-byte row (0: none)
     uint32_t batch_tot[MAXSEQ / 32 + 1];
-    uint16_t anchors[MAXSEQ / 64 + 2];                   // 64-sequence anchors
-    uint16_t anchors8[8];                                // then up to seven 8-sequence anchors
-    uint16_t tail[8];                                    // then up to seven single sequences
+    uint16_t anchors[MAXSEQ / 64 + 2];                   // 64-sequence anchors (the last one starts the tail of < 64)
     alignas(8) uint64_t bar[2];
-    uint32_t nanch, nanch8, ntail, end_kind, end_pos, first_bad, unit, abort, span_end;
+    uint32_t nanch, ntail, end_kind, end_pos, first_bad, unit, abort, span_end;
 };
 
 struct TSeq { uint32_t nxt, lit, ll, ml, off; };         // chunk-relative indices; nxt == kTNone: irregular
@@ -90,8 +88,6 @@ struct TileState {
     uint32_t par;            // mbarrier parities (bit b = next phase of buffer b); persists across units
     uint32_t pend;           // bit b: a load into buffer b is in flight
     int32_t bufc[2];         // chunk held by / in flight into each buffer
-    int32_t tabc;            // chunk the link tables describe
-    uint32_t pused;          // P entries the previous group wrote (cleared before the next one)
     bool last;
 };
 
@@ -386,10 +382,12 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     tile_wait_buf(sh, st, b);
     TP(0);
 
-    // ---- links: n1 = next token; 2/4/8-hop links by pointer doubling (n8 ends up in ta), then 16/32/64
-    //      (n64 in tb).  Every thread owns 8 positions; loads are issued together, stores afterwards.
-    if (st.tabc != chunk) {
+    // ---- links: n1 = next token, then 2/4/8/16/32/64-hop links by pointer doubling.  n1, n8 (ta) and n64 (tb)
+    //      have their own tables, n2/n4/n16/n32 live in the four quarters of the pointer table P, which is free
+    //      until the copies start.  Every thread owns 8 positions; loads are issued together, stores afterwards.
+    {
         constexpr int kPer = kTChunk / kTThreads;
+        uint16_t* const S0 = sh.P, *const S1 = sh.P + kTChunk, *const S2 = sh.P + 2 * kTChunk, *const S3 = sh.P + 3 * kTChunk;
         uint32_t v[kPer];
 #pragma unroll
         for (int j = 0; j < kPer; j++) {
@@ -400,86 +398,49 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
 #pragma unroll
         for (int j = 0; j < kPer; j++) sh.n1[tid + j * kTThreads] = (uint16_t)v[j];
         __syncthreads();
-#pragma unroll
-        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.n1[v[j]];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) sh.ta[tid + j * kTThreads] = (uint16_t)v[j];                  // n2
+#define LLC_TILE_DOUBLE(FROM, TO)                                                                     \
+        _Pragma("unroll") for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : FROM[v[j]]; \
+        _Pragma("unroll") for (int j = 0; j < kPer; j++) TO[tid + j * kTThreads] = (uint16_t)v[j];     \
         __syncthreads();
-#pragma unroll
-        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.ta[v[j]];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) sh.tb[tid + j * kTThreads] = (uint16_t)v[j];                  // n4
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.tb[v[j]];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) sh.ta[tid + j * kTThreads] = (uint16_t)v[j];                  // n8
-        __syncthreads();
-        // n16 and n32 by two more doublings (the pointer table P is free at this point), n64 from n32
-#pragma unroll
-        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.ta[v[j]];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) sh.P[tid + j * kTThreads] = (uint16_t)v[j];                   // n16
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.P[v[j]];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) sh.P[kTChunk + tid + j * kTThreads] = (uint16_t)v[j];         // n32
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < kPer; j++) v[j] = v[j] >= kTChunk ? kTNone : sh.P[kTChunk + v[j]];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) sh.tb[tid + j * kTThreads] = (uint16_t)v[j];                  // n64
-        st.pused = max(st.pused, 2u * kTChunk);                          // cleared again before the copies
-        st.tabc = chunk;
-        __syncthreads();
+        LLC_TILE_DOUBLE(sh.n1, S0)                           // n2
+        LLC_TILE_DOUBLE(S0, S1)                              // n4
+        LLC_TILE_DOUBLE(S1, sh.ta)                           // n8
+        LLC_TILE_DOUBLE(sh.ta, S2)                           // n16
+        LLC_TILE_DOUBLE(S2, S3)                              // n32
+        LLC_TILE_DOUBLE(S3, sh.tb)                           // n64
+#undef LLC_TILE_DOUBLE
         TC(0, 1);
     }
     TP(1);
 
-    // ---- chase: 64-sequence anchors, then 8-sequence anchors, then single steps up to the chunk exit or
-    //      the first irregular token
+    // ---- chase: one thread follows the 64-hop links from the chunk entry, then finds how many more regular
+    //      sequences there are (< 64) by descending through the 32/16/8/4/2/1-hop links
     if (tid == 0) {
-        uint32_t p = st.ip - cbase, na = 0, na8 = 0, nt = 0, kind = 0;   // kind 0: left the chunk, 1: irregular token at p
-        uint32_t n;
-        while (p < kTChunk && na < MAXSEQ / 64 - 2 && (n = sh.tb[p]) != kTNone) { sh.anchors[na++] = (uint16_t)p; p = n; }
-        while (p < kTChunk && na8 < 7 && (n = sh.ta[p]) != kTNone) { sh.anchors8[na8++] = (uint16_t)p; p = n; }
-        while (p < kTChunk && nt < 7) {
-            n = sh.n1[p];
-            if (n == kTNone) { kind = 1; break; }
-            sh.tail[nt++] = (uint16_t)p;
-            p = n;
-        }
-        sh.nanch = na; sh.nanch8 = na8; sh.ntail = nt; sh.end_kind = kind; sh.end_pos = p;
+        const uint16_t* const S0 = sh.P, *const S1 = sh.P + kTChunk, *const S2 = sh.P + 2 * kTChunk, *const S3 = sh.P + 3 * kTChunk;
+        uint32_t p = st.ip - cbase, na = 0, rem = 0, n;
+        while (p < kTChunk && na < MAXSEQ / 64 - 1 && (n = sh.tb[p]) != kTNone) { sh.anchors[na++] = (uint16_t)p; p = n; }
+        sh.anchors[na] = (uint16_t)p;                                // the tail starts here
+        if (p < kTChunk && (n = S3[p]) != kTNone) { rem += 32; p = n; }
+        if (p < kTChunk && (n = S2[p]) != kTNone) { rem += 16; p = n; }
+        if (p < kTChunk && (n = sh.ta[p]) != kTNone) { rem += 8; p = n; }
+        if (p < kTChunk && (n = S1[p]) != kTNone) { rem += 4; p = n; }
+        if (p < kTChunk && (n = S0[p]) != kTNone) { rem += 2; p = n; }
+        if (p < kTChunk && (n = sh.n1[p]) != kTNone) { rem += 1; p = n; }
+        // kind 0: left the chunk (or the group is full), 1: irregular token at p
+        sh.nanch = na; sh.ntail = rem; sh.end_kind = (p < kTChunk && sh.n1[p] == kTNone) ? 1u : 0u; sh.end_pos = p;
         sh.first_bad = 0xffffffffu;
     }
     sh.startbits[tid] = 0;                                           // kTRows == kTThreads
     if (tid == 0) sh.row2seq[0] = 0;
-    for (uint32_t j = tid * 8u; j < st.pused; j += kTThreads * 8u) *reinterpret_cast<uint4*>(&sh.P[j]) = make_uint4(0, 0, 0, 0);
-    st.pused = 0;
     __syncthreads();
-    const uint32_t nanch = sh.nanch, ntail = sh.ntail;
-    const uint32_t n8a = nanch * 8u + sh.nanch8;                     // 8-sequence runs
-    const uint32_t nseq = n8a * 8u + ntail;
+    const uint32_t nanch = sh.nanch;
+    const uint32_t nseq = nanch * 64u + sh.ntail;
     const uint32_t end_ip = cbase + sh.end_pos;
     const bool end_special = sh.end_kind != 0;
     TP(2);
     TC(1, 1); TC(2, nseq);
     if (sh.abort) return -1;
     if (nseq == 0) { st.ip = end_ip; return 1; }                     // irregular token right at st.ip
-
-    // ---- expand into sequence starts: one thread per 8-sequence run
-    if (tid < n8a) {
-        uint32_t p;
-        if (tid < nanch * 8u) {
-            p = sh.anchors[tid >> 3];
-            for (uint32_t h = tid & 7u; h; h--) p = sh.ta[p];
-        } else p = sh.anchors8[tid - nanch * 8u];
-#pragma unroll
-        for (int j = 0; j < 8; j++) { sh.seq_start[tid * 8u + j] = (uint16_t)p; p = sh.n1[p]; }
-    }
-    if (tid < ntail) sh.seq_start[n8a * 8u + tid] = sh.tail[tid];
-    __syncthreads();
     TP(3);
 
     // ---- fields + lengths, scanned to output positions
@@ -489,7 +450,19 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     for (int r = 0; r < kRounds; r++) {
         const uint32_t bt = warp + r * kTWarps, k = bt * 32u + lane;
         uint32_t ll = 0, ml = 0, off = 0, lit = 0;
-        if (k < nseq) { const TSeq s = Fmt::parse(bp, sh.seq_start[k]); ll = s.ll; ml = s.ml; off = s.off; lit = s.lit; }
+        if (k < nseq) {
+            // sequence k = anchor (k / 64) + (k % 64) hops, taken as at most one 32/16/8/4/2/1-hop link each
+            const uint16_t* const S0 = sh.P, *const S1 = sh.P + kTChunk, *const S2 = sh.P + 2 * kTChunk, *const S3 = sh.P + 3 * kTChunk;
+            uint32_t p = sh.anchors[k >> 6];
+            if (k & 32u) p = S3[p];
+            if (k & 16u) p = S2[p];
+            if (k & 8u) p = sh.ta[p];
+            if (k & 4u) p = S1[p];
+            if (k & 2u) p = S0[p];
+            if (k & 1u) p = sh.n1[p];
+            sh.seq_start[k] = (uint16_t)p;
+            const TSeq s = Fmt::parse(bp, p); ll = s.ll; ml = s.ml; off = s.off; lit = s.lit;
+        }
         const uint32_t len = ll + ml;
         const uint32_t incl = warp_incl_sum(len, lane);
         f_len[r] = ll | (ml << 16); f_src[r] = off | (lit << 16); f_dl[r] = incl - len;
@@ -506,6 +479,9 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
         if (lane + 32u < nbatch) sh.batch_tot[lane + 32] = s1 - v1;
     }
     __syncthreads();
+    // the link tables are done with: P back to "nothing written"
+#pragma unroll
+    for (uint32_t j = 0; j < kTSpan / (8u * kTThreads); j++) *reinterpret_cast<uint4*>(&sh.P[(tid + j * kTThreads) * 8u]) = make_uint4(0, 0, 0, 0);
     // Span indices are relative to `base`, the 16-byte unit that holds the first byte of the group, so that
     // aligned units of the span are aligned units of the ring and of the output.
     const uint32_t op0 = st.op, base = op0 & ~15u, a0 = op0 - base;
@@ -537,7 +513,6 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     const uint32_t g_hi = base + gend;
     const uint32_t ring_lo = g_hi > kTRing ? g_hi - kTRing : 0u;     // older bytes have left the ring (they are flushed)
     const uint32_t nrows = (gend + 31u) >> 5;
-    st.pused = (gend + 7u) & ~7u;
 
     // ---- every output byte finds its source.  Warp w takes rows w, w + 16, ...; lane = byte of the row.
     //      The ring is only read here (sources older than the group); the group's own bytes collect in P and
@@ -640,7 +615,7 @@ __device__ __forceinline__ int64_t tile_decode_unit(TileShared<Fmt>& sh, uint32_
     st.gout = out - st.a;
     st.cap = st.a + min(cap, kTCapMax);
     st.ip = pad; st.op = st.a; st.flushed = st.a;
-    st.par = par; st.pend = 0; st.bufc[0] = st.bufc[1] = -1; st.tabc = -1; st.pused = kTSpan;
+    st.par = par; st.pend = 0; st.bufc[0] = st.bufc[1] = -1;
     st.last = last;
     // Tokens take the fast path up to the end of the stream; the parse itself keeps the closing sequences
     // (and anything that would read past the end) for the checked step (Fmt::ends_inside).
