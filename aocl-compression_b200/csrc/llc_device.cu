@@ -47,12 +47,13 @@ struct aocl_gpu_ctx_s {
     int decode_blocks = 0;          // persistent grid size of decode_parts_kernel
     int ws_blocks = 0;              // persistent grid size of decode_parts_ws_kernel
     // Decoder organisation (AOCL_GPU_DECODER).  Measured on B200, 1 GiB frames (LZ4 text / Snappy log):
-    //   tile   (default) one 512-thread CTA per partition, lane per sequence:    11.2 ms  / 8.5 ms
+    //   tile   (default) one 512-thread CTA per partition, thread per byte:      6.6 ms   / 5.4 ms  (first version: 11.2 / 8.5)
     //   warp   one warp per partition: LZ4 TMA-ring pipelined decoder            14.2 ms  / 11.9 ms
     //   ws     parser warp + lane-per-sequence copier warp per partition:        16-19 ms / 15.5 ms
     //   bundle 32 lane-parsers + 16 copier warps per CTA:                        22 ms    / 18 ms
     int decoder_mode = 4;
-    int pages_mode = 1;             // batched pages: a million independent units keep warp-per-page busy; env overrides
+    int pages_mode = 4;             // batched pages: tile decoder too since the thread-per-byte rewrite (262,144 x 64 KiB
+                                    // pages: LZ4 100 GB/s vs 66 GB/s warp-per-page, Snappy 155 vs 138); env overrides
     bool lz4_frameless = false;
     const uint32_t* in_flag = nullptr;   // one-shot input watermark for the next compress (aocl_gpu_set_input_watermark)
     bool batch_mode = false;        // last enqueue was a batch call (finish() returns -failures)

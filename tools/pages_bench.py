@@ -73,7 +73,7 @@ for codec, name in [(c, nm) for c, nm in ((0, "lz4"), (4, "snappy")) if nm in ar
         assert torch.equal(d_out[r * P * PS:(r + 1) * P * PS], d_in), r
     C = int(csz.sum())
     print(json.dumps({"workload": f"{N} independent 64 KiB {name} pages (BASELINE configs[4]); {P} distinct pages x{R} replicas of the compressed bytes",
-                      "decoder": os.environ.get("AOCL_GPU_DECODER", "warp (default for pages)"),
+                      "decoder": os.environ.get("AOCL_GPU_DECODER", "tile (default)"),
                       "decompress_ms": best_d, "decompress_GBps": N * PS / best_d / 1e6, "pages_per_s": N / best_d * 1e3,
                       "compress_ms_16384_pages": best_c, "compress_GBps": P * PS / best_c / 1e6, "ratio": C / (P * PS),
                       "hbm_algorithmic_GBps": (N * PS + C * R) / best_d / 1e6}))
