@@ -39,6 +39,7 @@ struct aocl_gpu_ctx_s {
     int stab_ctas_per_sm = -1;      // AOCL_GPU_STAB_CTAS: shared-table CTAs per SM (-1 auto, 0 never; max 14)
     size_t l2_persist_bytes = 0, l2_window_bytes = 0;
     int snappy_gtab_ctas_per_sm = -1;   // AOCL_GPU_SNAPPY_GTAB_CTAS: Snappy global-table CTAs per SM (-1 auto, 0 never)
+    int snappy_stab_ctas_per_sm = -1;   // AOCL_GPU_SNAPPY_STAB_CTAS: Snappy shared-memory-table CTAs per SM (-1 auto)
     int sm_count = 0;
     uint8_t* ws = nullptr;          // growable HBM workspace (scratch slots, tables, plans)
     size_t ws_bytes = 0;
@@ -123,6 +124,7 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     }
     if (const char* e = getenv("AOCL_GPU_GTAB_CTAS")) c->gtab_ctas_per_sm = atoi(e);
     if (const char* e = getenv("AOCL_GPU_SNAPPY_GTAB_CTAS")) c->snappy_gtab_ctas_per_sm = atoi(e);
+    if (const char* e = getenv("AOCL_GPU_SNAPPY_STAB_CTAS")) c->snappy_stab_ctas_per_sm = atoi(e);
     if (const char* e = getenv("AOCL_GPU_STAB_CTAS")) c->stab_ctas_per_sm = atoi(e) > kStabMax ? kStabMax : atoi(e);
 
     // opt in to the shared-memory sizes the encoders need (16 KiB LZ4 table, 32 KiB Snappy table)
@@ -385,11 +387,23 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
         const SnappyGeom g = snappy_geom(n, T);
         const uint32_t F = g.frags_total;
         const uint64_t slot = 76544;                           // >= 32 + 65536 + 65536/6, multiple of 256
-        // same placement rule as the LZ4 encoder: fragments are serial chains, the 32 KiB table caps
-        // the shared-memory flavour at 7 warps per SM, the global-table flavour runs snappy_gtab per SM
-        int sn_gtab = c->snappy_gtab_ctas_per_sm;
-        if (sn_gtab < 0) sn_gtab = F > (uint32_t)c->sm_count * 6u ? 24 : 0;   // measured (lean encoder): 12 -> 40.3 ms, 16 -> 32.8, 20 -> 31.3, 24 -> 29.2, 28 -> 45.6 (tables outgrow L2)
-        const uint32_t g_grid = (uint32_t)sn_gtab * (uint32_t)c->sm_count < F ? (uint32_t)sn_gtab * (uint32_t)c->sm_count : F;
+        // Fragments are serial chains, so what counts is how many are resident at once.  A shared-memory-table
+        // warp costs 33.5 KiB of shared memory (32 KiB table + claim bits), a global-table warp 1.5 KiB plus 32 KiB
+        // of L2 (beyond ~24 per SM = 116 MB the tables outgrow L2).  Small frames run shared-memory warps only (6 per
+        // SM), larger ones global-table warps only.  Both flavours CAN run side by side on two streams sharing the
+        // fragment ticket (AOCL_GPU_SNAPPY_STAB_CTAS), but measured on B200 24 + 5 per SM is no faster than 24 + 0
+        // (28.1 ms per GiB either way): the two kernels need different shared-memory carve-outs, so they do not share
+        // an SM, and forcing the large carve-out on the global-table warps costs them the L1 that serves their
+        // candidate fetches (29 -> 40 ms).
+        int sn_gtab = c->snappy_gtab_ctas_per_sm, sn_stab = c->snappy_stab_ctas_per_sm;
+        const bool small = F <= (uint32_t)c->sm_count * 6u;
+        if (sn_gtab < 0) sn_gtab = small ? 0 : 24;   // measured (lean encoder, global tables only): 12 -> 40.3 ms, 16 -> 32.8, 20 -> 31.3, 24 -> 29.2, 28 -> 45.6
+        if (sn_stab < 0) sn_stab = small ? 6 : (sn_gtab > 0 ? 0 : 6);
+        if (sn_stab > 6) sn_stab = 6;
+        if (sn_gtab == 0 && sn_stab == 0) sn_stab = 6;
+        const uint32_t a_grid = (uint32_t)sn_stab * (uint32_t)c->sm_count < F ? (uint32_t)sn_stab * (uint32_t)c->sm_count : F;
+        const uint32_t g_want = F - a_grid < (uint32_t)sn_gtab * (uint32_t)c->sm_count ? F - a_grid : (uint32_t)sn_gtab * (uint32_t)c->sm_count;
+        const uint32_t g_grid = g_want;
         const size_t o_len = 0, o_off = align_up(o_len + sizeof(uint32_t) * (F + 2), 256);
         const size_t o_tab = align_up(o_off + sizeof(uint64_t) * (F + 1), 256);
         const size_t o_scr = align_up(o_tab + (size_t)g_grid * 32768, 256);
@@ -400,24 +414,32 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
         uint16_t* tables = reinterpret_cast<uint16_t*>(c->ws + o_tab);
         uint8_t* scratch = c->ws + o_scr;
         cudaMemsetAsync(ticket, 0, sizeof(uint32_t), c->stream);
-        if (F && g_grid && c->l2_persist_bytes) {              // keep the hash tables resident in L2
-            cudaStreamAttrValue av = {};
-            av.accessPolicyWindow.base_ptr = tables;
-            const size_t used = (size_t)g_grid * 32768;
-            av.accessPolicyWindow.num_bytes = used < c->l2_window_bytes ? used : c->l2_window_bytes;
-            const double ratio = (double)c->l2_persist_bytes / (double)av.accessPolicyWindow.num_bytes;
-            av.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        const int enc_slot = prof_begin(c, "snappy_encode_frags_kernel");   // brackets both flavours (fork .. join)
+        if (g_grid) {
+            // fork: the global-table flavour runs on the side stream
+            cudaEventRecord(c->ev_fork, c->stream);
+            cudaStreamWaitEvent(c->side, c->ev_fork, 0);
+            if (c->l2_persist_bytes) {                         // keep the hash tables resident in L2
+                cudaStreamAttrValue av = {};
+                av.accessPolicyWindow.base_ptr = tables;
+                const size_t used = (size_t)g_grid * 32768;
+                av.accessPolicyWindow.num_bytes = used < c->l2_window_bytes ? used : c->l2_window_bytes;
+                const double ratio = (double)c->l2_persist_bytes / (double)av.accessPolicyWindow.num_bytes;
+                av.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(c->side, cudaStreamAttributeAccessPolicyWindow, &av);
+            }
+            snappy_encode_frags_gtab_kernel<<<g_grid, 32, 0, c->side>>>(src, g, scratch, slot, frag_len, ticket, tables, in_flag, c->d_res);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            cudaEventRecord(c->ev_join, c->side);
         }
-        if (F && g_grid) LLC_LAUNCH(snappy_encode_frags_gtab_kernel, g_grid, 32, 0, c->stream, src, g, scratch, slot, frag_len, ticket, tables, in_flag, c->d_res);
-        else if (F) LLC_LAUNCH(snappy_encode_frags_kernel, (F < (uint32_t)c->sm_count * 6u ? F : (uint32_t)c->sm_count * 6u), 32, 32768,
-                               c->stream, src, g, scratch, slot, frag_len, ticket, in_flag, c->d_res);
-        if (F && g_grid && c->l2_persist_bytes) {              // later kernels on this stream: no window
-            cudaStreamAttrValue av = {};
-            cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        if (a_grid) {
+            snappy_encode_frags_kernel<<<a_grid, 32, 32768, c->stream>>>(src, g, scratch, slot, frag_len, ticket, in_flag, c->d_res);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
         }
+        if (g_grid) cudaStreamWaitEvent(c->stream, c->ev_join, 0);
+        prof_end(c, enc_slot);
         LLC_LAUNCH(snappy_plan_kernel, 1, 1024, 0, c->stream, g, frag_len, frag_off, dst, (uint64_t)out_cap, c->d_res);
         if (F) LLC_LAUNCH(snappy_compact_kernel, F, 256, 0, c->stream, scratch, slot, frag_len, frag_off, dst, c->d_res);
     }

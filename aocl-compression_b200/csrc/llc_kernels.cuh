@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(32) encode_pages_kernel(int codec, const uint8
                                                           const uint32_t* __restrict__ out_caps, long long* status,
                                                           uint64_t count, CallResult* res) {
     extern __shared__ __align__(16) uint32_t tab_mem[];
-    __shared__ uint8_t own_mem[kLeanOwnBytes];
+    __shared__ __align__(16) uint8_t own_mem[kLeanOwnBytes];   // LZ4: owner bytes; Snappy: claim bits
     const int lane = lane_id();
     for (uint64_t i = blockIdx.x; i < count; i += gridDim.x) {
         const uint8_t* in = in_ptrs[i];
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(32) encode_pages_kernel(int codec, const uint8
             op = __shfl_sync(kFull, op, 0);
             for (uint32_t p = 0; p < n; p += kSnappyBlock) {
                 op += snappy_encode_fragment_lean(in + p, min(kSnappyBlock, n - p), dst + op,
-                                                  reinterpret_cast<uint16_t*>(tab_mem), own_mem, lane);
+                                                  reinterpret_cast<uint16_t*>(tab_mem), reinterpret_cast<uint32_t*>(own_mem), lane);
                 __syncwarp();
             }
             got = op;
@@ -642,7 +642,7 @@ __device__ __forceinline__ void snappy_locate(const SnappyGeom& g, uint32_t f, u
 
 __device__ __forceinline__ void snappy_encode_frags_loop(const uint8_t* __restrict__ src, const SnappyGeom& g, uint8_t* scratch,
                                                          uint64_t slot, uint32_t* frag_len, uint32_t* ticket, uint16_t* tab,
-                                                         uint8_t* own, const uint32_t* in_flag, CallResult* res) {
+                                                         uint32_t* claim, const uint32_t* in_flag, CallResult* res) {
     const int lane = lane_id();
     InGate gate(in_flag, &res->error);                       // watermark: bytes present from the start of the input
     for (;;) {
@@ -653,7 +653,7 @@ __device__ __forceinline__ void snappy_encode_frags_loop(const uint8_t* __restri
         uint32_t part, len; uint64_t off;
         snappy_locate(g, f, &part, &off, &len);
         gate.wait((uint32_t)(off + len));
-        const uint32_t got = snappy_encode_fragment_lean(src + off, len, scratch + slot * f, tab, own, lane);
+        const uint32_t got = snappy_encode_fragment_lean(src + off, len, scratch + slot * f, tab, claim, lane);
         if (lane == 0) frag_len[f] = got;
         __syncwarp();
     }
@@ -662,15 +662,15 @@ __global__ void __launch_bounds__(32) snappy_encode_frags_kernel(const uint8_t* 
                                                                  uint8_t* scratch, uint64_t slot, uint32_t* frag_len,
                                                                  uint32_t* ticket, const uint32_t* in_flag, CallResult* res) {
     extern __shared__ __align__(16) uint32_t tab_mem[];
-    __shared__ uint8_t own_mem[kLeanOwnBytes];
-    snappy_encode_frags_loop(src, g, scratch, slot, frag_len, ticket, reinterpret_cast<uint16_t*>(tab_mem), own_mem, in_flag, res);
+    __shared__ uint32_t claim_mem[kSnappyClaimBytes / 4];
+    snappy_encode_frags_loop(src, g, scratch, slot, frag_len, ticket, reinterpret_cast<uint16_t*>(tab_mem), claim_mem, in_flag, res);
 }
 __global__ void __launch_bounds__(32) snappy_encode_frags_gtab_kernel(const uint8_t* __restrict__ src, SnappyGeom g,
                                                                       uint8_t* scratch, uint64_t slot, uint32_t* frag_len,
                                                                       uint32_t* ticket, uint16_t* tables,
                                                                       const uint32_t* in_flag, CallResult* res) {
-    __shared__ uint8_t own_mem[kLeanOwnBytes];
-    snappy_encode_frags_loop(src, g, scratch, slot, frag_len, ticket, tables + (size_t)blockIdx.x * 16384, own_mem, in_flag, res);
+    __shared__ uint32_t claim_mem[kSnappyClaimBytes / 4];
+    snappy_encode_frags_loop(src, g, scratch, slot, frag_len, ticket, tables + (size_t)blockIdx.x * 16384, claim_mem, in_flag, res);
 }
 
 // Step 2: offsets of every fragment in the final stream, RAP frame and the leading varint

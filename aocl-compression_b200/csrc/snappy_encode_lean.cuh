@@ -6,8 +6,11 @@
 //   * the "insert ip-1, probe ip" that follows a copy (snappy.cc:1016-1032) is lanes 0 and 1 of the next
 //     round, in front of the first 30 probes of the next search (stride 1: skip runs 32..61), so every
 //     lane runs the same code;
-//   * same-bucket slots inside a round are detected with a 4 KiB owner-byte table in shared memory
-//     (keyed by the low 12 hash bits: conservative); MATCH.ANY only runs in rounds that have such a pair;
+//   * same-bucket slots inside a round are detected with a 512-byte claim bitmap in shared memory (one
+//     bit per value of the low 12 hash bits: conservative; ATOMS.OR returns whether another slot of the
+//     round already claimed the bit); MATCH.ANY only runs in rounds that have such a pair.  The bitmap
+//     replaced a 4 KiB owner-byte table so that shared-memory-table and global-table warps fit one SM
+//     together (llc_device.cu);
 //   * every lane verifies its own candidate (the u16 table has no room for check bits), so after one
 //     round the hit / no-hit answer of all 32 slots is known: a round without bucket clashes serves
 //     every element pair that starts inside its 32-position window -- the slots behind a copy are the
@@ -21,6 +24,8 @@
 #include "lz4_encode_lean.cuh"
 
 namespace llc {
+
+constexpr uint32_t kSnappyClaimBytes = 512;             // one claim bit per value of the low 12 hash bits
 
 struct SnappyPending { bool valid; uint32_t lit_from, mpos, off, len; };
 
@@ -52,12 +57,13 @@ __device__ __forceinline__ uint32_t snappy_lean_count(const LeanSrc& S, uint32_t
 }
 
 __device__ inline uint32_t snappy_encode_fragment_lean(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst,
-                                                       uint16_t* tab, uint8_t* own, int lane) {
+                                                       uint16_t* tab, uint32_t* claim, int lane) {
     const LeanSrc S(src);
     uint32_t tsize = 256;                                   // snappy.cc:619-632
     if (n > 16384) tsize = 16384; else while (tsize < n) tsize <<= 1;
     const int shift = 32 - (31 - __clz(tsize));
     for (uint32_t i = lane; i < tsize / 2; i += 32) reinterpret_cast<uint32_t*>(tab)[i] = 0;
+    for (uint32_t i = lane; i < kSnappyClaimBytes / 4; i += 32) claim[i] = 0;     // all zero between rounds
     __syncwarp();
     uint32_t op = 0, anchor = 0;                            // anchor = next_emit: first byte not yet emitted
     if (n >= 15) {
@@ -90,16 +96,19 @@ __device__ inline uint32_t snappy_encode_fragment_lean(const uint8_t* __restrict
                 valid = ip + incl <= ip_limit;
             }
             uint32_t seq4 = 0, h = 0, cand = 0;
+            bool seen = false;
             if (valid) {
                 seq4 = S.u32(cur);
                 h = (seq4 * 0x1e35a7bdU) >> shift;          // snappy.cc:152-158
                 cand = tab[h];
-                own[h & (kLeanOwnBytes - 1u)] = (uint8_t)lane;
+                const uint32_t bit = 1u << (h & 31u);
+                seen = (atomicOr(&claim[(h >> 5) & (kSnappyClaimBytes / 4 - 1u)], bit) & bit) != 0;
             }
             // ---- the previous literal + copy is written out while the table gather is in flight
             if (pend.valid) { pend.valid = false; snappy_lean_emit(pend, src, dst, op, lane); }
+            const bool clashed = __any_sync(kFull, seen);
             __syncwarp();
-            const bool clashed = __any_sync(kFull, valid && own[h & (kLeanOwnBytes - 1u)] != (uint8_t)lane);
+            if (valid) claim[(h >> 5) & (kSnappyClaimBytes / 4 - 1u)] = 0;   // every claimant clears its word
             unsigned peers = 0;
             if (clashed) {                                  // two slots of this round (may) share a bucket
                 peers = __match_any_sync(kFull, valid ? h : (0x80000000u | (uint32_t)lane));
