@@ -173,3 +173,22 @@ def test_one_launch_many_partitions_per_cta(torch_mod, ctx, codec):
         torch.cuda.synchronize()
         assert ctx.decompress(codec, d_comp, csz, d_back) == n
         assert torch.equal(d_back, d_in)
+
+
+@pytest.mark.parametrize("codec", [kat.LZ4, kat.SNAPPY])
+def test_decode_is_deterministic_under_repetition(torch_mod, ctx, oracle, codec):
+    """The tile decoder resolves match sources with racy look-throughs and pointer jumping whose intermediate
+    states depend on warp timing; the bytes it produces must not.  Decode oracle-compressed streams of every
+    generator twenty times each and compare every result with the input."""
+    torch = torch_mod
+    for name in kat.GOLDEN_GENS:
+        data = kat.make_input(name, 3 * 262144 + 1234)
+        comp = oracle.compress(data, codec)
+        d_comp = dev(torch, np.frombuffer(comp, dtype=np.uint8))
+        d_in = dev(torch, data)
+        d_back = torch.zeros(len(data), dtype=torch.uint8, device="cuda")
+        for it in range(20):
+            d_back.fill_(0xA5)
+            torch.cuda.synchronize()
+            assert ctx.decompress(codec, d_comp, len(comp), d_back) == len(data), (name, it)
+            assert torch.equal(d_back, d_in), (name, it)
