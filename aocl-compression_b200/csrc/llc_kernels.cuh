@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(kBThreads, 1) decode_parts_bundle_kernel(int c
     }
 }
 
-// Tile variant (decode_tile.cuh): one 512-thread CTA per partition, lane per sequence, 64 KiB output
-// window in shared memory; partitions handed out through the atomic ticket.
+// Tile variant (decode_tile.cuh): one 512-thread CTA per partition, lane per sequence for the parse, thread
+// per byte for the copies, 32 KiB output window in shared memory; partitions handed out through the atomic ticket.
 template <class Fmt, bool SNAPPY>
 __global__ void __launch_bounds__(kTThreads, 2) decode_parts_tile_kernel(const uint8_t* __restrict__ in, uint8_t* out,
                                                                         const PartDesc* __restrict__ parts, CallResult* res,
