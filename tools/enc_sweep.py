@@ -22,7 +22,13 @@ def main():
     import llc_b200
     name = sys.argv[1] if len(sys.argv) > 1 else "lz4_text"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-    wl = bench.WORKLOADS[name]
+    extra = {  # further data shapes for perf sanity (not bench lines)
+        "lz4_mixed": dict(codec=0, gen="mixed_entropy", seed=1234, size=1 << 30),
+        "snappy_mixed": dict(codec=4, gen="mixed_entropy", seed=1234, size=1 << 30),
+        "lz4_log": dict(codec=0, gen="log_like", seed=2025, size=1 << 30),
+        "snappy_text": dict(codec=4, gen="text_like", seed=2024, size=1 << 30),
+    }
+    wl = bench.WORKLOADS.get(name) or extra[name]
     cache = f"/dev/shm/llc_{name}_{wl['size']}.npy"
     if os.path.exists(cache):
         data = np.load(cache)
