@@ -568,10 +568,12 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     TP(6);
     if (sh.abort) return -1;
 
-    // ---- P -> ring: aligned 16-byte units in one piece (32 bytes of P -> 16 bytes of ring), the partial
-    //      units at both ends byte by byte
+    // ---- P -> ring and HBM: aligned 16-byte units in one piece (32 bytes of P -> 16 bytes of ring and of the
+    //      output), the partial unit at the head byte by byte together with what the previous flush left in the
+    //      ring (< 16 bytes); a partial unit at the tail stays in the ring for the next flush.
     {
         const uint32_t u_lo = (a0 + 15u) >> 4, u_hi = gend >> 4;      // full units [u_lo, u_hi)
+        uint4* const g4 = reinterpret_cast<uint4*>(st.gout + base);
         for (uint32_t u = u_lo + tid; u < u_hi; u += kTThreads) {
             const uint4 lo = *reinterpret_cast<const uint4*>(&sh.P[u << 4]);
             const uint4 hi = *reinterpret_cast<const uint4*>(&sh.P[(u << 4) + 8u]);
@@ -579,18 +581,25 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
             o.x = __byte_perm(lo.x, lo.y, 0x6420); o.y = __byte_perm(lo.z, lo.w, 0x6420);
             o.z = __byte_perm(hi.x, hi.y, 0x6420); o.w = __byte_perm(hi.z, hi.w, 0x6420);
             *reinterpret_cast<uint4*>(&sh.ring[(base + (u << 4)) & kTRingMask]) = o;
+            g4[u] = o;
         }
+        const bool tail_kept = u_hi >= u_lo;                          // the tail starts at an aligned unit
         if (tid < 16u) {
             const uint32_t xh = tid;                                 // head unit (unit 0 when the group starts inside it)
-            if (xh >= a0 && xh < min(gend, u_lo << 4)) sh.ring[(base + xh) & kTRingMask] = (uint8_t)sh.P[xh];
+            if (xh >= a0 && xh < min(gend, u_lo << 4)) {
+                const uint8_t v = (uint8_t)sh.P[xh];
+                sh.ring[(base + xh) & kTRingMask] = v;
+                st.gout[base + xh] = v;
+            }
             const uint32_t xt = (u_hi << 4) + tid;                   // tail unit
             if (xt >= max(a0, u_lo << 4) && xt < gend) sh.ring[(base + xt) & kTRingMask] = (uint8_t)sh.P[xt];
+        } else if (tid < 32u) {
+            const uint32_t pos = st.flushed + (tid - 16u);           // left in the ring by the previous flush
+            if (pos < op0) st.gout[pos] = sh.ring[pos & kTRingMask];
         }
+        st.flushed = tail_kept ? base + (u_hi << 4) : g_hi;
     }
     __syncthreads();
-
-    // ---- ring -> HBM
-    tile_flush(sh, st, g_hi, false);
     st.op = g_hi;
     TP(7);
     if (nexec == nseq) { st.ip = end_ip; return end_special ? 1 : 0; }
