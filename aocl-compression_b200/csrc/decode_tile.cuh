@@ -114,6 +114,7 @@ constexpr uint32_t kTSpinMax = 1u << 22;
 struct TileLz4 {
     static constexpr int kMaxSeq = 1024;                 // sequences per group (a 4 KiB chunk of text holds ~700)
     static constexpr bool kHasLit = true;                // a sequence carries literals and a match
+    static constexpr bool kSetupPairs = false;           // per-byte source step: one row per trip
     static constexpr uint32_t kEndSlack = 12;            // regular sequences end >= 12 bytes before the capacity
 
     __device__ static __forceinline__ TSeq parse(const uint8_t* bp, uint32_t i) {
@@ -141,6 +142,7 @@ struct TileLz4 {
 struct TileSnappy {
     static constexpr int kMaxSeq = 1280;                 // elements per group (a 4 KiB chunk of text holds ~1200); sized to keep 2 CTAs per SM
     static constexpr bool kHasLit = false;               // an element is either literals or a copy
+    static constexpr bool kSetupPairs = true;            // per-byte source step: two rows per trip
     static constexpr uint32_t kEndSlack = 0;
 
     // one element = one "sequence" with either literals or a copy
@@ -339,7 +341,7 @@ __device__ __forceinline__ void tile_wait_buf(TileShared<Fmt>& sh, TileState& st
 }
 // Caller guarantees (with a __syncthreads) that nobody still reads buffer b.
 template <class Fmt>
-__device__ __forceinline__ void tile_issue_buf(TileShared<Fmt>& sh, TileState& st, int b, int32_t chunk) {
+__device__ __forceinline__ void tile_issue_buf(TileShared<Fmt>& sh, TileState& st, int b, int32_t chunk, uint32_t elected = 0) {
     if (st.pend & (1u << b)) {
         // At most one load per buffer in flight.  EVERY thread has to observe the old phase before thread 0
         // re-arms the barrier: a warp that polls late would otherwise find the barrier two phases on, read
@@ -353,8 +355,10 @@ __device__ __forceinline__ void tile_issue_buf(TileShared<Fmt>& sh, TileState& s
     if (base >= st.iend) return;
     const uint32_t left = st.iend - base;
     const uint32_t bytes = left >= kTBuf ? kTBuf : ((left + 15u) & ~15u);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == elected) {
+#ifndef LLC_T_NOFENCE
         fence_proxy_async();
+#endif
         mbar_expect_tx(&sh.bar[b], bytes);
         bulk_g2s(sh.inbuf[b], st.gin + base, bytes, &sh.bar[b]);
     }
@@ -378,7 +382,6 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     TP_DECL
     __syncthreads();                                                 // previous phase is done with both buffers
     if (st.bufc[b] != chunk) tile_issue_buf(sh, st, b, chunk);
-    if (st.bufc[b ^ 1] != chunk + 1 && cbase + kTChunk < st.iend) tile_issue_buf(sh, st, b ^ 1, chunk + 1);
     tile_wait_buf(sh, st, b);
     TP(0);
 
@@ -412,6 +415,10 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
         TC(0, 1);
     }
     TP(1);
+
+    // ---- prefetch of the next chunk, issued by a thread of warp 1 (idle during the chase); nobody has read the
+    //      other buffer since the previous group
+    if (st.bufc[b ^ 1] != chunk + 1 && cbase + kTChunk < st.iend) tile_issue_buf(sh, st, b ^ 1, chunk + 1, 32u);
 
     // ---- chase: one thread follows the 64-hop links from the chunk entry, then finds how many more regular
     //      sequences there are (< 64) by descending through the 32/16/8/4/2/1-hop links
@@ -522,7 +529,52 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
     //      No data-dependent branches: the literal and the old-source byte come through one load with a selected
     //      address, the look at P goes to entry a0 (harmless) when the byte does not need it.
     uint32_t unres = 0;                                              // bit i: my byte of row warp + 16 i still follows a pointer
-    {
+    if constexpr (Fmt::kSetupPairs) {
+        // two rows per trip, loads before stores (Snappy: 5.30 -> 5.11 ms per GiB; LZ4 prefers one row, whose
+        // look-through sees more of the rows in front of it: 6.42 vs 6.66 ms)
+        const uint32_t le_mask = (2u << lane) - 2u;
+        uint32_t bit = 1u;
+        for (uint32_t row0 = warp; row0 < nrows; row0 += 2u * kTWarps, bit <<= 2) {
+            uint32_t xs[2], ks[2], es[2], ps[2], vs[2], pas[2];
+            bool live[2], ing[2], far[2];
+            uint2 qs[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t row = row0 + (uint32_t)u * kTWarps;
+                xs[u] = (row << 5) + lane;
+                live[u] = row < nrows && xs[u] >= a0 && xs[u] < gend;
+                ks[u] = 0;
+                if (row < nrows) ks[u] = (uint32_t)sh.row2seq[row] + (uint32_t)__popc(sh.startbits[row] & le_mask) - 1u;
+                if (!live[u]) ks[u] = 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) qs[u] = sh.sq[ks[u]];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t r = xs[u] - (qs[u].x & 0xffffu), ll = qs[u].x >> 16;
+                pas[u] = base + xs[u] - (qs[u].y & 0xffffu);
+                const bool is_lit = r < ll;
+                ing[u] = live[u] && !is_lit && pas[u] >= op0;
+                far[u] = live[u] && !is_lit && pas[u] < ring_lo;
+                const uint8_t* vp = is_lit ? bp + (qs[u].y >> 16) + r : sh.ring + (pas[u] & kTRingMask);
+                vs[u] = *vp;
+                ps[u] = ing[u] ? pas[u] - base : a0;
+                es[u] = sh.P[ps[u]];
+            }
+            if (__any_sync(kFull, far[0] || far[1])) {
+                if (far[0]) vs[0] = __ldcg(st.gout + pas[0]);
+                if (far[1]) vs[1] = __ldcg(st.gout + pas[1]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                uint32_t e = es[u];
+                if (e == 0) e = kTPtr | ps[u];
+                if (!ing[u]) e = kTKnown | vs[u];
+                if (live[u]) sh.P[xs[u]] = (uint16_t)e;
+                if (live[u] && e < kTKnown) unres |= bit << u;
+            }
+        }
+    } else {
         const uint32_t le_mask = (2u << lane) - 2u;                  // bits 1 .. lane
         uint32_t bit = 1u;
         for (uint32_t row = warp; row < nrows; row += kTWarps, bit <<= 1) {
