@@ -356,9 +356,7 @@ __device__ __forceinline__ void tile_issue_buf(TileShared<Fmt>& sh, TileState& s
     const uint32_t left = st.iend - base;
     const uint32_t bytes = left >= kTBuf ? kTBuf : ((left + 15u) & ~15u);
     if (threadIdx.x == elected) {
-#ifndef LLC_T_NOFENCE
         fence_proxy_async();
-#endif
         mbar_expect_tx(&sh.bar[b], bytes);
         bulk_g2s(sh.inbuf[b], st.gin + base, bytes, &sh.bar[b]);
     }
