@@ -49,7 +49,6 @@ struct BShared {
     uint32_t bundle;
 };
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // Copier loads do not allocate in L1: the 28 parsers of a CTA live off L1-resident lines of their
 // compressed streams, and the copiers' match reads (random 64 KiB windows) would evict them.
 __device__ __forceinline__ uint32_t ld_na_u8(const uint8_t* p) {

@@ -26,6 +26,8 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int64_t kErrCorrupt = -2;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// Pull the line that holds p into L1 (no register result)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 // ---- unaligned little-endian loads built from aligned words ---------------------------
 // The aligned words touched always overlap the requested byte range, so they stay inside
