@@ -1,0 +1,211 @@
+"""Executable model of the tile decoder (aocl-compression_b200/csrc/decode_tile.cuh) in numpy: the same
+phases on the same data structures -- per-position "next token" links, pointer doubling to 64-hop links,
+the chase with binary descent, sequence starts by binary-decomposed hops, block scan, start bitmap + covering
+sequence per 32-byte row, the per-byte source step with look-through into already written entries, pointer
+jumping over the 16-bit pointer/value table, flush -- so that the algorithm (not the CUDA code) can be
+checked against the oracle on the CPU, where this container has no GPU.  Two schedules of the source step
+are modelled: every earlier row already written ("front") and no row written yet ("none"); the real kernel
+is somewhere in between, and the bytes must not depend on it.
+
+Only the regular path is modelled; an irregular sequence (a length that needs a 255 extension byte, the
+closing sequences of a block) ends the group and is executed by a plain sequential step, as in the kernel.
+Test infrastructure only (tests/test_tile_model.py)."""
+from __future__ import annotations
+
+import numpy as np
+
+CHUNK = 4096
+MARGIN = 384
+SPAN = 16384
+NONE = 0xFFFF
+PTR = 0x4000
+KNOWN = 0xFF00
+MAXSEQ = 1024
+RING = 32768
+
+
+def _links_lz4(bp: np.ndarray, cbase: int, iend: int):
+    """n1 for every byte position of the chunk (TileLz4::parse + ends_inside)."""
+    i = np.arange(CHUNK)
+    tok = bp[i].astype(np.int64)
+    e1 = bp[i + 1].astype(np.int64)
+    nib_l, nib_m = tok >> 4, tok & 15
+    ext_l, ext_m = nib_l == 15, nib_m == 15
+    ll = nib_l + np.where(ext_l, e1, 0)
+    lit = i + 1 + ext_l
+    q = lit + ll
+    e2 = bp[np.minimum(q + 2, len(bp) - 1)].astype(np.int64)
+    special = (ext_l & (e1 == 255)) | (ext_m & (e2 == 255))
+    nxt = q + 2 + ext_m
+    ok = (cbase + i < iend) & ~special & (cbase + lit + ll + 8 <= iend)
+    return np.where(ok, nxt, NONE).astype(np.int64)
+
+
+def _fields_lz4(bp: np.ndarray, p: np.ndarray):
+    tok = bp[p].astype(np.int64)
+    e1 = bp[p + 1].astype(np.int64)
+    nib_l, nib_m = tok >> 4, tok & 15
+    ext_l, ext_m = nib_l == 15, nib_m == 15
+    ll = nib_l + np.where(ext_l, e1, 0)
+    lit = p + 1 + ext_l
+    q = lit + ll
+    off = bp[q].astype(np.int64) | (bp[q + 1].astype(np.int64) << 8)
+    ml = 4 + nib_m + np.where(ext_m, bp[q + 2].astype(np.int64), 0)
+    return ll, ml, off, lit
+
+
+def _double(tbl: np.ndarray) -> np.ndarray:
+    inside = tbl < CHUNK
+    return np.where(inside, tbl[np.where(inside, tbl, 0)], NONE)
+
+
+def _slow_sequence_lz4(src: np.ndarray, ip: int, out: bytearray, cap: int, iend: int):
+    """One checked sequence (tile_slow_step_lz4 for a last/vanilla block).  Returns (ip, done)."""
+    tok = int(src[ip]); ip += 1
+    ll = tok >> 4
+    if ll == 15:
+        while True:
+            b = int(src[ip]); ip += 1; ll += b
+            if b != 255:
+                break
+    out += src[ip:ip + ll].tobytes(); ip += ll
+    if ip >= iend:
+        return ip, True
+    off = int(src[ip]) | (int(src[ip + 1]) << 8); ip += 2
+    ml = tok & 15
+    if ml == 15:
+        while True:
+            b = int(src[ip]); ip += 1; ml += b
+            if b != 255:
+                break
+    ml += 4
+    assert 0 < off <= len(out)
+    for _ in range(ml):
+        out.append(out[-off])
+    return ip, False
+
+
+def decode_lz4_block(stream: bytes, cap: int, a: int = 0, schedule: str = "front", stats: dict | None = None) -> bytes:
+    """Decode one LZ4 block the way the tile decoder does; `a` is the output alignment (out & 15)."""
+    src = np.frombuffer(stream, dtype=np.uint8)
+    iend = len(src)
+    padded = np.concatenate([src, np.zeros(CHUNK + MARGIN + 8, dtype=np.uint8)])
+    out = bytearray()                                         # out[j] = output position a + j
+    ip = 0
+    groups = rounds = 0
+    while True:
+        # ---------------- one group ----------------
+        chunk = ip >> 12
+        cbase = chunk << 12
+        bp = padded[cbase:cbase + CHUNK + MARGIN + 8]
+        slow = True
+        if ip < iend:
+            n1 = _links_lz4(bp, cbase, iend)
+            n2 = _double(n1); n4 = _double(n2); n8 = _double(n4); n16 = _double(n8); n32 = _double(n16); n64 = _double(n32)
+            # chase: 64-hop anchors, then binary descent
+            p = ip - cbase
+            anchors = []
+            while p < CHUNK and len(anchors) < MAXSEQ // 64 - 1 and n64[p] != NONE:
+                anchors.append(p); p = int(n64[p])
+            anchors.append(p)
+            rem = 0
+            for tbl, w in ((n32, 32), (n16, 16), (n8, 8), (n4, 4), (n2, 2), (n1, 1)):
+                if p < CHUNK and tbl[p] != NONE:
+                    rem += w; p = int(tbl[p])
+            end_special = p < CHUNK and n1[p] == NONE
+            end_ip = cbase + p
+            nseq = (len(anchors) - 1) * 64 + rem
+            if nseq:
+                # sequence starts by binary-decomposed hops
+                k = np.arange(nseq)
+                sp = np.array(anchors, dtype=np.int64)[k >> 6]
+                for tbl, w in ((n32, 32), (n16, 16), (n8, 8), (n4, 4), (n2, 2), (n1, 1)):
+                    sp = np.where(k & w, tbl[sp], sp)
+                ll, ml, off, lit = _fields_lz4(bp, sp)
+                ln = ll + ml
+                op0 = a + len(out)
+                base = op0 & ~15
+                a0 = op0 - base
+                dl = op0 + np.concatenate([[0], np.cumsum(ln)[:-1]])
+                dm = dl + ll
+                end = dm + ml
+                lim_o = min(a + cap - 12, base + SPAN) if a + cap >= op0 + 12 else 0
+                bad = (off == 0) | (off > dm - a) | (end > lim_o)
+                nexec = int(np.argmax(bad)) if bad.any() else nseq
+                if nexec:
+                    rel = (dl - base)[:nexec]
+                    gend = int((end - base)[nexec - 1])
+                    nrows = (gend + 31) >> 5
+                    # start bitmap + 1 + covering sequence per row
+                    startbits = np.zeros(nrows + 1, dtype=np.uint64)
+                    np.bitwise_or.at(startbits, rel >> 5, np.uint64(1) << (rel & 31).astype(np.uint64))
+                    row2seq = np.zeros(nrows + 1, dtype=np.int64)
+                    erel = (end - base)[:nexec]
+                    for kk in range(nexec):
+                        for R in range((int(rel[kk]) + 31) >> 5, nrows):
+                            if (R << 5) >= erel[kk]:
+                                break
+                            row2seq[R] = kk + 1
+                    # per-byte source step
+                    P = np.zeros(SPAN, dtype=np.int64)
+                    x = np.arange(nrows * 32)
+                    lane = x & 31
+                    le_mask = ((np.uint64(2) << lane.astype(np.uint64)) - np.uint64(2)) & np.uint64(0xFFFFFFFF)
+                    bits = startbits[x >> 5] & le_mask
+                    pop = np.array([bin(int(b)).count("1") for b in bits])
+                    kx = row2seq[x >> 5] + pop - 1
+                    live = (x >= a0) & (x < gend)
+                    kx = np.where(live, kx, 0)
+                    r = x - rel[kx]
+                    is_lit = live & (r >= 0) & (r < ll[kx])
+                    pa = base + x - off[kx]
+                    in_group = live & ~is_lit & (pa >= op0)
+                    pre = live & ~is_lit & ~in_group
+                    vals = np.zeros(len(x), dtype=np.int64)
+                    vals[is_lit] = bp[(lit[kx] + r)[is_lit]]
+                    if pre.any():
+                        hist = np.frombuffer(bytes(out), dtype=np.uint8)
+                        vals[pre] = hist[(pa - a)[pre]]               # ring or, beyond 32 KiB back, L2: same bytes
+                    if schedule == "none":                            # nobody has written anything yet
+                        e = np.where(in_group, PTR | (pa - base), KNOWN | vals)
+                        P[x[live]] = e[live]
+                    else:                                             # every earlier ROW has been written
+                        for row in range(nrows):
+                            s = slice(row * 32, row * 32 + 32)
+                            pp = np.where(in_group[s], (pa - base)[s], a0)
+                            look = P[pp]
+                            e = np.where(look == 0, PTR | pp, look)
+                            e = np.where(in_group[s], e, KNOWN | vals[s])
+                            P[x[s][live[s]]] = e[live[s]]
+                    # pointer jumping, two jumps per round
+                    idx = x[live]
+                    while True:
+                        cur = P[idx]
+                        un = cur < KNOWN
+                        if not un.any():
+                            break
+                        rounds += 1
+                        t = idx[un]
+                        qv = P[P[t] - PTR]
+                        assert (qv != 0).all()
+                        q2 = np.where(qv < KNOWN, P[np.where(qv < KNOWN, qv - PTR, 0)], qv)
+                        P[t] = q2
+                    out += (P[a0:gend] & 255).astype(np.uint8).tobytes()
+                    groups += 1
+                    if nexec == nseq:
+                        ip = end_ip
+                        slow = bool(end_special)
+                    else:
+                        ip = cbase + int(sp[nexec])
+                        slow = True
+                else:
+                    slow = True
+            else:
+                ip = end_ip
+        if slow:
+            ip, done = _slow_sequence_lz4(padded, ip, out, cap, iend)
+            if done:
+                break
+    if stats is not None:
+        stats.update(groups=groups, rounds=rounds)
+    return bytes(out)
