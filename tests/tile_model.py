@@ -5,7 +5,8 @@ sequence per 32-byte row, the per-byte source step with look-through into alread
 jumping over the 16-bit pointer/value table, flush -- so that the algorithm (not the CUDA code) can be
 checked against the oracle on the CPU, where this container has no GPU.  Two schedules of the source step
 are modelled: every earlier row already written ("front") and no row written yet ("none"); the real kernel
-is somewhere in between, and the bytes must not depend on it.
+is somewhere in between (schedule "16": waves of 16 rows that cannot see each other, one row per warp), and
+the bytes must not depend on it.
 
 Only the regular path is modelled; an irregular sequence (a length that needs a 255 extension byte, the
 closing sequences of a block) ends the group and is executed by a plain sequential step, as in the kernel.
@@ -92,7 +93,7 @@ def decode_lz4_block(stream: bytes, cap: int, a: int = 0, schedule: str = "front
     padded = np.concatenate([src, np.zeros(CHUNK + MARGIN + 8, dtype=np.uint8)])
     out = bytearray()                                         # out[j] = output position a + j
     ip = 0
-    groups = rounds = 0
+    groups = rounds = visits = 0
     while True:
         # ---------------- one group ----------------
         chunk = ip >> 12
@@ -169,14 +170,26 @@ def decode_lz4_block(stream: bytes, cap: int, a: int = 0, schedule: str = "front
                     if schedule == "none":                            # nobody has written anything yet
                         e = np.where(in_group, PTR | (pa - base), KNOWN | vals)
                         P[x[live]] = e[live]
-                    else:                                             # every earlier ROW has been written
-                        for row in range(nrows):
-                            s = slice(row * 32, row * 32 + 32)
-                            pp = np.where(in_group[s], (pa - base)[s], a0)
+                    else:                                             # every earlier WAVE of rows has been written
+                        # "front": one row at a time; "<w>": waves of w adjacent rows run side by side (the kernel: 16, one
+                        # row per warp); "block<w>": the span is cut into w contiguous blocks, one per warp, and the
+                        # warps walk their blocks in step
+                        if schedule.startswith("block"):
+                            nb = int(schedule[5:])
+                            per = -(-nrows // nb)
+                            steps = [[b * per + i for b in range(nb) if b * per + i < min(nrows, (b + 1) * per)] for i in range(per)]
+                        else:
+                            wave = 1 if schedule == "front" else int(schedule)
+                            steps = [list(range(r0, min(nrows, r0 + wave))) for r0 in range(0, nrows, wave)]
+                        for rows_now in steps:
+                            if not rows_now:
+                                continue
+                            sel = np.concatenate([np.arange(r * 32, r * 32 + 32) for r in rows_now])
+                            pp = np.where(in_group[sel], (pa - base)[sel], a0)
                             look = P[pp]
                             e = np.where(look == 0, PTR | pp, look)
-                            e = np.where(in_group[s], e, KNOWN | vals[s])
-                            P[x[s][live[s]]] = e[live[s]]
+                            e = np.where(in_group[sel], e, KNOWN | vals[sel])
+                            P[x[sel][live[sel]]] = e[live[sel]]
                     # pointer jumping, two jumps per round
                     idx = x[live]
                     while True:
@@ -186,6 +199,7 @@ def decode_lz4_block(stream: bytes, cap: int, a: int = 0, schedule: str = "front
                             break
                         rounds += 1
                         t = idx[un]
+                        visits += len(t)
                         qv = P[P[t] - PTR]
                         assert (qv != 0).all()
                         q2 = np.where(qv < KNOWN, P[np.where(qv < KNOWN, qv - PTR, 0)], qv)
@@ -207,5 +221,5 @@ def decode_lz4_block(stream: bytes, cap: int, a: int = 0, schedule: str = "front
             if done:
                 break
     if stats is not None:
-        stats.update(groups=groups, rounds=rounds)
+        stats.update(groups=groups, rounds=rounds, byte_rounds=visits / max(1, len(out)))
     return bytes(out)
