@@ -34,3 +34,22 @@ def test_model_decodes_oracle_streams(oracle, gen):
     assert tm.decode_lz4_block(stream, len(data), a=3, schedule="front", stats=front) == data.tobytes()
     assert tm.decode_lz4_block(stream, len(data), a=3, schedule="none", stats=none) == data.tobytes()
     assert front["rounds"] <= none["rounds"]                 # looking through written entries never costs rounds
+
+
+@pytest.mark.parametrize("profile", list(ss.PROFILES))
+@pytest.mark.parametrize("schedule", ["16", "none"])
+def test_model_decodes_synthetic_snappy_streams(oracle, profile, schedule):
+    stream = ss.snappy_stream(profile, 120_000, 9)
+    want = oracle.decompress(stream, kat.SNAPPY, 400_000)
+    assert want is not None
+    for a in (0, 11):
+        assert tm.decode_snappy_stream(stream, a=a, schedule=schedule) == want, (profile, schedule, a)
+
+
+@pytest.mark.parametrize("gen", ["log", "text"])
+def test_model_decodes_oracle_snappy_streams(oracle, gen):
+    data = kat.make_input(gen, 200_000)                      # below the RAP threshold: one raw stream
+    stream = oracle.compress(data, kat.SNAPPY)
+    st = {}
+    assert tm.decode_snappy_stream(stream, a=9, schedule="16", stats=st) == data.tobytes()
+    assert st["groups"] > 0

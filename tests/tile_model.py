@@ -8,7 +8,8 @@ are modelled: every earlier row already written ("front") and no row written yet
 is somewhere in between (schedule "16": waves of 16 rows that cannot see each other, one row per warp), and
 the bytes must not depend on it.
 
-Only the regular path is modelled; an irregular sequence (a length that needs a 255 extension byte, the
+LZ4 blocks and raw Snappy streams (one element per "sequence") share everything but the parse.  Only the regular
+path is modelled; an irregular sequence (a length that needs a 255 extension byte, the
 closing sequences of a block) ends the group and is executed by a plain sequential step, as in the kernel.
 Test infrastructure only (tests/test_tile_model.py)."""
 from __future__ import annotations
@@ -86,8 +87,84 @@ def _slow_sequence_lz4(src: np.ndarray, ip: int, out: bytearray, cap: int, iend:
     return ip, False
 
 
+def _links_snappy(bp: np.ndarray, cbase: int, iend: int):
+    """n1 for every byte position of the chunk (TileSnappy::parse + ends_inside): one element per hop."""
+    i = np.arange(CHUNK)
+    tag = bp[i].astype(np.int64)
+    b1 = bp[i + 1].astype(np.int64)
+    kind, v = tag & 3, tag >> 2
+    nxt = np.full(CHUNK, NONE, dtype=np.int64)
+    lit_s = (kind == 0) & (v < 60)
+    lit_1 = (kind == 0) & (v == 60)
+    nxt = np.where(lit_s, i + 1 + v + 1, nxt)
+    nxt = np.where(lit_1, i + 2 + b1 + 1, nxt)
+    nxt = np.where(kind == 1, i + 2, nxt)
+    nxt = np.where(kind == 2, i + 3, nxt)
+    ok = (cbase + i < iend) & (nxt != NONE) & (cbase + nxt <= iend)
+    return np.where(ok, nxt, NONE).astype(np.int64)
+
+
+def _fields_snappy(bp: np.ndarray, p: np.ndarray):
+    tag = bp[p].astype(np.int64)
+    b1 = bp[p + 1].astype(np.int64)
+    b2 = bp[p + 2].astype(np.int64)
+    kind, v = tag & 3, tag >> 2
+    ll = np.where(kind == 0, np.where(v < 60, v + 1, b1 + 1), 0)
+    lit = np.where((kind == 0) & (v == 60), p + 2, p + 1)
+    ml = np.where(kind == 1, 4 + (v & 7), np.where(kind == 2, 1 + v, 0))
+    off = np.where(kind == 1, ((tag >> 5) << 8) | b1, np.where(kind == 2, b1 | (b2 << 8), 0))
+    return ll, ml, off, lit
+
+
+def _slow_element_snappy(src: np.ndarray, ip: int, out: bytearray, cap: int, iend: int):
+    """One checked element (tile_slow_step_snappy).  Returns (ip, done)."""
+    if ip >= iend:
+        assert len(out) == cap
+        return ip, True
+    tag = int(src[ip]); ip += 1
+    kind = tag & 3
+    if kind == 0:
+        n = (tag >> 2) + 1
+        if n > 60:
+            nb = n - 60
+            n = int.from_bytes(src[ip:ip + nb].tobytes(), "little") + 1
+            ip += nb
+        out += src[ip:ip + n].tobytes()
+        return ip + n, False
+    if kind == 1:
+        n, off = 4 + ((tag >> 2) & 7), ((tag >> 5) << 8) | int(src[ip]); ip += 1
+    elif kind == 2:
+        n, off = 1 + (tag >> 2), int(src[ip]) | (int(src[ip + 1]) << 8); ip += 2
+    else:
+        n, off = 1 + (tag >> 2), int.from_bytes(src[ip:ip + 4].tobytes(), "little"); ip += 4
+    assert 0 < off <= len(out)
+    for _ in range(n):
+        out.append(out[-off])
+    return ip, False
+
+
+LZ4_FMT = dict(links=_links_lz4, fields=_fields_lz4, slow=_slow_sequence_lz4, end_slack=12, max_seq=1024)
+SNAPPY_FMT = dict(links=_links_snappy, fields=_fields_snappy, slow=_slow_element_snappy, end_slack=0, max_seq=1280)
+
+
 def decode_lz4_block(stream: bytes, cap: int, a: int = 0, schedule: str = "front", stats: dict | None = None) -> bytes:
     """Decode one LZ4 block the way the tile decoder does; `a` is the output alignment (out & 15)."""
+    return _decode(LZ4_FMT, stream, cap, a, schedule, stats)
+
+
+def decode_snappy_stream(stream: bytes, a: int = 0, schedule: str = "front", stats: dict | None = None) -> bytes:
+    """Decode a raw Snappy stream (varint length + elements) the way the tile decoder does."""
+    total, shift, n = 0, 0, 0
+    while True:
+        b = stream[n]; n += 1
+        total |= (b & 127) << shift
+        shift += 7
+        if b < 128:
+            break
+    return _decode(SNAPPY_FMT, stream[n:], total, a, schedule, stats)
+
+
+def _decode(fmt: dict, stream: bytes, cap: int, a: int, schedule: str, stats: dict | None) -> bytes:
     src = np.frombuffer(stream, dtype=np.uint8)
     iend = len(src)
     padded = np.concatenate([src, np.zeros(CHUNK + MARGIN + 8, dtype=np.uint8)])
@@ -101,12 +178,12 @@ def decode_lz4_block(stream: bytes, cap: int, a: int = 0, schedule: str = "front
         bp = padded[cbase:cbase + CHUNK + MARGIN + 8]
         slow = True
         if ip < iend:
-            n1 = _links_lz4(bp, cbase, iend)
+            n1 = fmt["links"](bp, cbase, iend)
             n2 = _double(n1); n4 = _double(n2); n8 = _double(n4); n16 = _double(n8); n32 = _double(n16); n64 = _double(n32)
             # chase: 64-hop anchors, then binary descent
             p = ip - cbase
             anchors = []
-            while p < CHUNK and len(anchors) < MAXSEQ // 64 - 1 and n64[p] != NONE:
+            while p < CHUNK and len(anchors) < fmt["max_seq"] // 64 - 1 and n64[p] != NONE:
                 anchors.append(p); p = int(n64[p])
             anchors.append(p)
             rem = 0
@@ -122,7 +199,7 @@ def decode_lz4_block(stream: bytes, cap: int, a: int = 0, schedule: str = "front
                 sp = np.array(anchors, dtype=np.int64)[k >> 6]
                 for tbl, w in ((n32, 32), (n16, 16), (n8, 8), (n4, 4), (n2, 2), (n1, 1)):
                     sp = np.where(k & w, tbl[sp], sp)
-                ll, ml, off, lit = _fields_lz4(bp, sp)
+                ll, ml, off, lit = fmt["fields"](bp, sp)
                 ln = ll + ml
                 op0 = a + len(out)
                 base = op0 & ~15
@@ -130,8 +207,9 @@ def decode_lz4_block(stream: bytes, cap: int, a: int = 0, schedule: str = "front
                 dl = op0 + np.concatenate([[0], np.cumsum(ln)[:-1]])
                 dm = dl + ll
                 end = dm + ml
-                lim_o = min(a + cap - 12, base + SPAN) if a + cap >= op0 + 12 else 0
-                bad = (off == 0) | (off > dm - a) | (end > lim_o)
+                slack = fmt["end_slack"]
+                lim_o = min(a + cap - slack, base + SPAN) if a + cap >= op0 + slack else 0
+                bad = ((ml != 0) & ((off == 0) | (off > dm - a))) | (end > lim_o)
                 nexec = int(np.argmax(bad)) if bad.any() else nseq
                 if nexec:
                     rel = (dl - base)[:nexec]
@@ -217,7 +295,7 @@ def decode_lz4_block(stream: bytes, cap: int, a: int = 0, schedule: str = "front
             else:
                 ip = end_ip
         if slow:
-            ip, done = _slow_sequence_lz4(padded, ip, out, cap, iend)
+            ip, done = fmt["slow"](padded, ip, out, cap, iend)
             if done:
                 break
     if stats is not None:
