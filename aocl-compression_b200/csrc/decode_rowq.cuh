@@ -1,0 +1,467 @@
+// decode_rowq.cuh -- row decoder: LANE PARSERS feeding THREAD-PER-BYTE ROW COPIERS through
+// shared-memory queues.  One CTA keeps kQSlots independent units (RAP partitions or pages) in
+// flight at once; nothing in it is CTA-wide (no __syncthreads after start-up, no pointer jumping).
+//
+// Why.  A unit is one serial token chain.  The tile decoder (decode_tile.cuh) breaks the chain with
+// a data-parallel parse (pointer doubling over every byte position) and resolves in-group match
+// sources with pointer jumping: 46 warp instructions per 10-byte sequence, 4 % of the HBM roofline.
+// With >= ~5 units per SM in flight there is a cheaper organisation:
+//
+//   warp 0        PARSERS, one LANE per unit.  Each lane walks its own token chain with scalar code:
+//                 one unaligned 8-byte window per sequence (two aligned 8-byte loads through L1,
+//                 issued as soon as the token tells where the next sequence starts), every validity
+//                 check of the reference decoders (lz4.c:3806-4305; snappy.cc:1466-1570, 2185-2199),
+//                 and one 16-byte record {literal position, literal length, offset, match length}
+//                 pushed into the unit's queue.  One warp instruction advances kQSlots chains.
+//   warps 1..28   COPIERS, one warp per unit.  A copier takes 32 records at a time (lane per record:
+//                 a warp scan of the lengths gives the output positions), then walks the output in
+//                 aligned 32-byte ROWS, lane per byte: byte x finds its record from the start bits
+//                 of the row (REDUX.OR + popc), fetches the record's fields with three shuffles and
+//                 takes its value from the TMA-staged input ring (literal), from the unit's 4 KiB
+//                 output ring in shared memory (match source in the last 4 KiB), from L2 (older
+//                 source) or -- a source inside the same row -- by pointer doubling over shuffles
+//                 (<= 5 rounds, only in rows that have such a byte).  Rows are executed in order, so
+//                 every other source is final when it is read; the row goes to the output ring and
+//                 to HBM (one full 32-byte sector per store instruction).
+//
+// The compressed stream reaches the copier through the TMA bulk-copy ring of in_ring.cuh
+// (cp.async.bulk + mbarrier, 4 x 512 B per unit); the parser lanes read the same lines through L1.
+// Queues are single-producer / single-consumer rings; unit boundaries travel in-band as marker
+// records, so a parser lane starts its next unit (atomic ticket) while the copier is still busy.
+//
+// Accept / reject behaviour and produced bytes are identical to the warp decoders
+// (lz4_decode_ring.cuh, snappy_codec.cuh) and through them to the reference.
+#pragma once
+#include "in_ring.cuh"
+#include "snappy_codec.cuh"
+
+namespace llc {
+
+constexpr int kQSlots = 28;                                  // units in flight per CTA = copier warps
+constexpr int kQThreads = 32 * (kQSlots + 1);
+constexpr uint32_t kQCap = 64, kQMask = kQCap - 1;           // records per unit queue
+constexpr uint32_t kQStride = kQCap + 1;                     // +1 record: parser lanes hit different banks
+constexpr uint32_t kORing = 4096, kORingMask = kORing - 1;   // output bytes kept in shared memory per unit
+constexpr uint32_t kQMarker = 0xffffffffu;                   // rec.y of a marker record: rec.w = kind, rec.x = argument
+constexpr uint32_t kQBegin = 1u, kQQuit = 2u;
+constexpr uint32_t kQCapMax = 0xfffe0000u;                  // positions + ring size must not wrap
+constexpr uint32_t kQSpinMax = 1u << 23;                     // copier watchdog (~1 s of polling)
+constexpr uint32_t kUnitBad = 0x100u;                        // QUnit.flags: the unit header itself is malformed
+
+struct QShared {
+    alignas(128) uint8_t oring[kQSlots][kORing];
+    alignas(128) uint8_t idata[kQSlots][kRingBytes];
+    uint4 q[kQSlots * kQStride];
+    alignas(8) uint64_t ibar[kQSlots][kStages];
+    volatile uint32_t tail[kQSlots];                         // records published by the parser lane
+    volatile uint32_t head[kQSlots];                         // records retired by the copier
+    volatile uint32_t done[kQSlots];                         // the parser lane has published its last record
+    volatile uint32_t abort;                                 // watchdog: a queue made no progress, everybody leaves
+};
+static_assert(sizeof(QShared) <= 227 * 1024, "row decoder shared memory");
+
+struct QUnit { const uint8_t* in; uint8_t* out; uint32_t clen, cap, flags; };
+
+// Units = partitions [first, first + n) of a parsed RAP frame.
+struct QPartsSource {
+    const uint8_t* in; uint8_t* out; const PartDesc* parts; CallResult* res; uint32_t first; uint64_t origin;
+    __device__ __forceinline__ bool open(uint32_t i, QUnit& u) const {
+        const PartDesc d = parts[first + i];
+        u.in = in + d.in_off; u.out = out + (d.out_off - origin); u.clen = d.in_len; u.cap = d.out_len; u.flags = d.flags;
+        return d.in_len != 0;                                // zero-length partitions are skipped (threads.c:264-268)
+    }
+    __device__ __forceinline__ void report(uint32_t i, int64_t got, const QUnit& u) const {
+        if (got < 0 || ((u.flags & kPartExact) && (uint64_t)got != u.cap)) atomicCAS(&res->error, 0, (int)(first + i) + 1);
+        else if (!(u.flags & kPartExact)) res->value = got;  // frame-less LZ4: size is whatever was produced
+    }
+    __device__ __forceinline__ void fail() const { atomicCAS(&res->error, 0, 0x7fffffff); }
+};
+// Units = independent frame-less pages.
+template <bool SNAPPY>
+struct QPagesSource {
+    const uint8_t* const* in_ptrs; const uint32_t* in_sizes; uint8_t* const* out_ptrs; const uint32_t* out_caps;
+    long long* status; CallResult* res;
+    __device__ __forceinline__ bool open(uint32_t i, QUnit& u) const {
+        u.in = in_ptrs[i]; u.out = out_ptrs[i]; u.clen = in_sizes[i]; u.cap = out_caps[i]; u.flags = kPartLast;
+        if (SNAPPY) {
+            uint32_t total = 0;
+            const uint32_t vb = get_varint32(u.in, u.clen, &total);
+            if (vb == 0 || total > u.cap) u.flags |= kUnitBad;
+            else { u.in += vb; u.clen -= vb; u.cap = total; u.flags |= kPartExact; }
+        }
+        return true;
+    }
+    __device__ __forceinline__ void report(uint32_t i, int64_t got, const QUnit&) const {
+        status[i] = got;
+        if (got < 0) atomicAdd(&res->error, 1);
+    }
+    __device__ __forceinline__ void fail() const { atomicAdd(&res->error, 1); }
+};
+
+// ----------------------------------------------------------------------------------------- parsers
+// 8 bytes at p, any alignment, from the two aligned 8-byte words that hold them.
+__device__ __forceinline__ uint64_t ldg_win64(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
+    const unsigned sh = (unsigned)(a & 7) * 8;
+    const uint64_t lo = w[0], hi = w[1];
+    return sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+}
+
+// Per-lane parser state (registers).  Positions are offsets from the unit's first byte.
+struct QLane {
+    const uint8_t* in;
+    uint32_t ip, iend, op, cap;
+    uint32_t fast_i_ex, fast_o_ex;     // exclusive bounds of the region where no end rule can fire
+    uint64_t w;                        // the 8 stream bytes at ip (valid when wvalid)
+    bool wvalid, last, bad;
+};
+
+__device__ __forceinline__ void qpush(uint4* q, uint32_t& tail, uint32_t lp, uint32_t ll, uint32_t off, uint32_t ml) {
+    q[tail & kQMask] = make_uint4(lp, ll, off, ml);
+    tail++;
+}
+
+// One LZ4 sequence for this lane.  Returns false when the unit is finished (ok or bad).
+__device__ __forceinline__ bool qlane_step_lz4(QLane& s, uint4* q, uint32_t& tail) {
+    const uint8_t* in = s.in;
+    const uint32_t ip = s.ip;
+    if (ip >= s.iend) { s.bad = true; return false; }
+    if ((ip < s.fast_i_ex) & (s.op < s.fast_o_ex)) {
+        // at least 319 stream bytes and 559 output bytes ahead: a sequence with at most one length byte each
+        // (ll <= 269, ml <= 273) cannot trigger an end-of-block rule and all its reads stay inside the stream
+        const uint64_t w = s.wvalid ? s.w : ldg_win64(in + ip);
+        const uint32_t w0 = (uint32_t)w;
+        const uint32_t tok = w0 & 0xffu, e1 = (w0 >> 8) & 0xffu;
+        const uint32_t nibL = tok >> 4, nibM = tok & 15u;
+        const bool extL = nibL == 15u, extM = nibM == 15u;
+        const uint32_t ll = nibL + (extL ? e1 : 0u);
+        const uint32_t hdr = 1u + (extL ? 1u : 0u);
+        const uint32_t rel = hdr + ll;                      // the offset field, relative to ip
+        uint32_t t;                                         // offset (2 bytes) and the byte after it
+        if (rel <= 5u) t = (uint32_t)(w >> (8u * rel));
+        else t = ld_u32(in + ip + rel);
+        const uint32_t off = t & 0xffffu, e2 = (t >> 16) & 0xffu;
+        if (!((extL & (e1 == 255u)) | (extM & (e2 == 255u)))) {
+            const uint32_t ipn = ip + rel + 2u + (extM ? 1u : 0u);
+            s.wvalid = ipn < s.fast_i_ex;
+            if (s.wvalid) s.w = ldg_win64(in + ipn);        // next window: in flight during the checks below
+            const uint32_t ml = nibM + 4u + (extM ? e2 : 0u);
+            const uint32_t op2 = s.op + ll;
+            if ((off - 1u) >= op2) { s.bad = true; return false; }       // lz4.c:4196-4197
+            qpush(q, tail, ip + hdr, ll, off, ml);
+            s.op = op2 + ml;
+            if ((ipn >> 7) != (ip >> 7)) prefetch_l1(in + ((ipn >> 7) + 2u) * 128u);
+            s.ip = ipn;
+            return true;
+        }
+    }
+    s.wvalid = false;
+    // general case: length runs, block tail, tiny units -- every check of the reference
+    const uint32_t tok = in[ip];
+    const uint32_t nibL = tok >> 4, nibM = tok & 15u;
+    const bool last = s.last;
+    const uint32_t iend = s.iend, cap = s.cap;
+    uint32_t p = ip + 1, ll = nibL;
+    if (ll == 15u) {
+        uint32_t b;
+        do { if (p >= iend) { s.bad = true; return false; } b = in[p++]; ll += b; } while (b == 255u && ll < 0x7fff0000u);
+    }
+    if (ll > iend - p || ll > cap - s.op) { s.bad = true; return false; }
+    const bool closing = ((uint64_t)s.op + ll + 12 > cap) || ((uint64_t)p + ll + 8 > iend);   // lz4.c:4104-4164
+    if (closing && last && p + ll != iend) { s.bad = true; return false; }
+    const uint32_t lit_pos = p;
+    s.op += ll;
+    const uint32_t qq = p + ll;
+    if ((closing && (last || s.op == cap)) || qq == iend) {
+        if (ll) qpush(q, tail, lit_pos, ll, 0, 0);
+        s.ip = qq;
+        return false;
+    }
+    if (qq + 2 > iend) { s.bad = true; return false; }
+    const uint32_t off = (uint32_t)in[qq] | ((uint32_t)in[qq + 1] << 8);
+    p = qq + 2;
+    uint32_t ml = nibM;
+    if (ml == 15u) {
+        uint32_t b;
+        do { if (p >= iend) { s.bad = true; return false; } b = in[p++]; ml += b; } while (b == 255u && ml < 0x7fff0000u);
+    }
+    ml += 4;
+    if (off == 0 || off > s.op || ml > cap - s.op) { s.bad = true; return false; }   // lz4.c:4196-4197
+    if (last && (uint64_t)s.op + ml + 5 > cap) { s.bad = true; return false; }       // lz4.c:4262-4264
+    qpush(q, tail, lit_pos, ll, off, ml);
+    s.op += ml;
+    s.ip = p;
+    prefetch_l1(in + ((p >> 7) + 1u) * 128u);
+    if (!last && (s.op == cap || p >= iend)) return false;                           // lz4.c:4285-4288
+    return true;
+}
+
+// One Snappy element for this lane (cap is the exact size the stream must produce).
+__device__ __forceinline__ bool qlane_step_snappy(QLane& s, uint4* q, uint32_t& tail) {
+    const uint8_t* in = s.in;
+    const uint32_t ip = s.ip, iend = s.iend, expect = s.cap;
+    if (ip >= iend) return false;
+    if (ip < s.fast_i_ex) {
+        const uint64_t w = s.wvalid ? s.w : ldg_win64(in + ip);
+        const uint32_t w0 = (uint32_t)w;
+        const uint32_t tag = w0 & 0xffu, b1 = (w0 >> 8) & 0xffu, b2 = (w0 >> 16) & 0xffu;
+        const uint32_t kind = tag & 3u, hi = tag >> 2;
+        if (kind != 3u && !(kind == 0u && hi >= 60u)) {
+            const bool is_lit = kind == 0u;
+            const uint32_t lit_len = hi + 1u;
+            const uint32_t ipn = ip + (is_lit ? 1u + lit_len : (kind == 1u ? 2u : 3u));
+            s.wvalid = ipn < s.fast_i_ex;
+            if (s.wvalid) s.w = ldg_win64(in + ipn);
+            const uint32_t cp_len = (kind == 1u) ? 4u + (hi & 7u) : 1u + hi;
+            const uint32_t cp_off = (kind == 1u) ? (((tag >> 5) << 8) | b1) : (b1 | (b2 << 8));
+            const uint32_t len = is_lit ? lit_len : cp_len;
+            if (len > expect - s.op || (!is_lit && (cp_off - 1u) >= s.op)) { s.bad = true; return false; }   // snappy.cc:2185-2199
+            qpush(q, tail, ip + 1u, is_lit ? lit_len : 0u, is_lit ? 0u : cp_off, is_lit ? 0u : cp_len);
+            s.op += len;
+            if ((ipn >> 7) != (ip >> 7)) prefetch_l1(in + ((ipn >> 7) + 2u) * 128u);
+            s.ip = ipn;
+            return true;
+        }
+    }
+    s.wvalid = false;
+    const uint32_t tag = in[ip];
+    const uint32_t kind = tag & 3u, hi = tag >> 2;
+    if (kind == 0u) {                                   // literal, snappy.cc:1492-1527
+        uint32_t len = hi + 1u, p = ip + 1u;
+        if (len > 60u) {
+            const uint32_t nb = len - 60u;
+            if (p + nb > iend) { s.bad = true; return false; }
+            uint32_t v = 0;
+            for (uint32_t k = 0; k < nb; k++) v |= (uint32_t)in[p + k] << (8 * k);
+            if (v == 0xffffffffu) { s.bad = true; return false; }
+            len = v + 1u; p += nb;
+        }
+        if (len > iend - p || len > expect - s.op) { s.bad = true; return false; }
+        qpush(q, tail, p, len, 0, 0);
+        s.op += len; s.ip = p + len;
+        prefetch_l1(in + ((s.ip >> 7) + 1u) * 128u);
+        return true;
+    }
+    uint32_t len, off, adv;                             // char_table, snappy-internal.h:406-439
+    if (kind == 1u) {
+        if (ip + 2 > iend) { s.bad = true; return false; }
+        len = 4u + (hi & 7u); off = ((tag >> 5) << 8) | in[ip + 1]; adv = 2;
+    } else if (kind == 2u) {
+        if (ip + 3 > iend) { s.bad = true; return false; }
+        len = 1u + hi; off = (uint32_t)in[ip + 1] | ((uint32_t)in[ip + 2] << 8); adv = 3;
+    } else {
+        if (ip + 5 > iend) { s.bad = true; return false; }
+        len = 1u + hi;
+        off = (uint32_t)in[ip + 1] | ((uint32_t)in[ip + 2] << 8) | ((uint32_t)in[ip + 3] << 16) | ((uint32_t)in[ip + 4] << 24);
+        adv = 5;
+    }
+    if (off == 0 || off > s.op || len > expect - s.op) { s.bad = true; return false; }   // snappy.cc:2185-2199
+    qpush(q, tail, ip + 1u, 0, off, len);
+    s.op += len; s.ip = ip + adv;
+    return true;
+}
+
+// The parser warp: lane l owns slot l.  A lane that finishes a unit reports its result and draws the next
+// one: the first unit of every slot is assigned statically (interleaved over the grid, so that a frame
+// with fewer units than slots spreads over all SMs), later ones come from the atomic ticket.
+template <bool SNAPPY, class Src>
+__device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, unsigned int* ticket, int lane) {
+    uint4* const q = sh.q + (lane < kQSlots ? lane : 0) * kQStride;
+    QLane s;
+    QUnit u;
+    s.in = nullptr; s.ip = s.iend = s.op = s.cap = s.fast_i_ex = s.fast_o_ex = 0; s.w = 0;
+    s.wvalid = false; s.last = false; s.bad = false;
+    u.in = nullptr; u.out = nullptr; u.clen = u.cap = u.flags = 0;
+    uint32_t tail = 0, published = 0, head_c = 0, cur = 0;
+    bool active = false, alive = lane < kQSlots, first_fetch = true;
+    while (__any_sync(kFull, alive)) {
+        if (sh.abort) break;
+        if (alive) {
+            if (tail - head_c >= kQCap) head_c = sh.head[lane];
+            if (tail - head_c < kQCap) {
+                if (!active) {
+                    uint32_t i;
+                    if (first_fetch) { i = (uint32_t)lane * gridDim.x + blockIdx.x; first_fetch = false; }
+                    else i = gridDim.x * (uint32_t)kQSlots + atomicAdd(ticket, 1u);
+                    if (i >= nunits) {
+                        qpush(q, tail, 0, kQMarker, 0, kQQuit);
+                        alive = false;
+                    } else if (src.open(i, u)) {
+                        cur = i;
+                        s.in = u.in; s.iend = u.clen; s.cap = min(u.cap, kQCapMax);
+                        s.ip = 0; s.op = 0; s.bad = false; s.wvalid = false;
+                        s.last = (u.flags & kPartLast) != 0;
+                        const bool any_fast = s.iend >= 320u && (SNAPPY || s.cap >= 560u);
+                        s.fast_i_ex = any_fast ? s.iend - 319u : 0u;
+                        s.fast_o_ex = (any_fast && !SNAPPY) ? s.cap - 559u : 0u;
+                        bool run = true;
+                        if (u.flags & kUnitBad) { s.bad = true; run = false; }
+                        else if (!SNAPPY) {
+                            if (s.iend == 0) { s.bad = true; run = false; }
+                            else if (s.cap == 0) { s.bad = !(s.iend == 1 && s.in[0] == 0); run = false; }   // lz4.c:3854-3858
+                        }
+                        if (run) {
+                            prefetch_l1(s.in + 128); prefetch_l1(s.in + 256);
+                            qpush(q, tail, i, kQMarker, 0, kQBegin);
+                            active = true;
+                        } else {
+                            src.report(cur, s.bad ? kErrCorrupt : 0, u);
+                        }
+                    }
+                } else {
+                    const bool more = SNAPPY ? qlane_step_snappy(s, q, tail) : qlane_step_lz4(s, q, tail);
+                    if (!more) {
+                        long long r = s.bad ? kErrCorrupt : (long long)s.op;
+                        if (!s.bad && SNAPPY && s.op != s.cap) r = kErrCorrupt;             // snappy.cc:1715
+                        src.report(cur, r, u);
+                        active = false;
+                    }
+                }
+            }
+            if (tail - published >= 16u || (!active && tail != published)) {
+                __threadfence_block();
+                sh.tail[lane] = tail;
+                published = tail;
+                if (!alive) { __threadfence_block(); sh.done[lane] = 1u; }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------- copiers
+// Executes the n (1..32) records held lane-per-record in `rec`; lanes >= n hold nothing.
+__device__ __forceinline__ void rowq_batch(Ring& ring, uint32_t obase, uint8_t* gout, uint32_t& op_io, uint32_t pad,
+                                           const uint4 rec, uint32_t n, int lane) {
+    const uint32_t op = op_io;
+    const bool valid = (uint32_t)lane < n;
+    const uint32_t ll = valid ? rec.y : 0u, ml = valid ? rec.w : 0u;
+    const uint32_t len = ll + ml;
+    const uint32_t incl = warp_incl_sum(len, lane);
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    const uint32_t d = op + incl - len;                      // first output byte of my record
+    const uint32_t D = valid ? d : 0xffffffffu;
+    const uint32_t M = d + ll;                               // first match byte of my record
+    const uint32_t lpos = rec.x + pad;                       // literals of my record in ring coordinates
+    const uint32_t L = lpos - d;                             // literal byte x of my record sits at ring position x + L
+    const uint32_t O = rec.z;
+    const uint32_t op_end = op + total;
+    // literal window of the batch (positions grow with the lane): the TMA ring when it fits, else global loads
+    const uint32_t lit_lo = __shfl_sync(kFull, lpos, 0);
+    const uint32_t lit_hi = __shfl_sync(kFull, lpos + ll, (int)n - 1);
+    const bool use_ring = lit_hi <= (lit_lo & ~(kChunk - 1u)) + kRingBytes;
+    if (use_ring) { ring.advance(lit_lo, lane); ring.ensure(lit_hi); }
+    const uint32_t sbase = smem_u32(ring.sm);
+    const uint8_t* const gin = ring.gbase;
+    const uint32_t lemask = (2u << lane) - 1u;               // bits 0 .. lane
+    for (uint32_t x0 = op & ~31u; x0 < op_end; x0 += 32u) {
+        const uint32_t x = x0 + (uint32_t)lane;
+        const bool live = (x - op) < total;
+        // which record covers byte x: records that start at or before x0, plus the starts inside the row up to x
+        const uint32_t rel = D - x0;
+        const uint32_t bits = __reduce_or_sync(kFull, rel < 32u ? (1u << rel) : 0u);
+        const uint32_t cnt0 = (uint32_t)__popc(__ballot_sync(kFull, D <= x0));
+        const uint32_t k = cnt0 - 1u + (uint32_t)__popc(bits & ~1u & lemask);
+        const uint32_t m = __shfl_sync(kFull, M, (int)k), l = __shfl_sync(kFull, L, (int)k), o = __shfl_sync(kFull, O, (int)k);
+        const bool is_lit = x < m;
+        const uint32_t src = x - o;
+        const bool mat = live && !is_lit;
+        const uint32_t rowlo = max(x0, op);
+        const bool dep = mat && src >= rowlo;                // source inside this row: not written yet
+        const bool far = mat && (src + kORing < x0 + 32u);   // source has left the output ring: read back from L2
+        uint32_t v = 0;
+        if (live && is_lit) {
+            if (use_ring) v = lds_u8(sbase + ((x + l) & kRingMask));
+            else v = gin[x + l];
+        }
+        if (mat && !dep && !far) v = lds_u8(obase + (src & kORingMask));
+        if (__any_sync(kFull, far)) { if (far) v = __ldcg(gout + src); }
+        if (__any_sync(kFull, dep)) {
+            // pointer doubling over the lanes of the row: a byte whose source lane is still unknown
+            // adopts that lane's source; every round at least halves the chains (<= 5 rounds)
+            uint32_t j = src - x0;
+            bool need = dep;
+            do {
+                const uint32_t vj = __shfl_sync(kFull, v, (int)j);
+                const uint32_t jj = __shfl_sync(kFull, j, (int)j);
+                const bool nj = __shfl_sync(kFull, need ? 1 : 0, (int)j) != 0;
+                if (need) { if (!nj) { v = vj; need = false; } else j = jj; }
+            } while (__any_sync(kFull, need));
+        }
+        if (live) {
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(obase + (x & kORingMask)), "r"(v) : "memory");
+            gout[x] = (uint8_t)v;
+        }
+        __syncwarp();
+    }
+    op_io = op_end;
+}
+
+// A copier warp: consumes the queue of its slot until the parser's QUIT marker.
+template <class Src>
+__device__ inline void rowq_copy(QShared& sh, const Src& src, int slot, int lane) {
+    Ring ring;
+    ring.init(sh.idata[slot], sh.ibar[slot], lane);
+    const uint32_t obase = smem_u32(sh.oring[slot]);
+    const uint4* const q = sh.q + slot * kQStride;
+    uint32_t head = 0, op = 0, pad = 0;
+    uint8_t* gout = nullptr;
+    bool open = false;
+    for (;;) {
+        uint32_t avail, spins = 0;
+        for (;;) {
+            const uint32_t fin = sh.done[slot];
+            __threadfence_block();
+            avail = sh.tail[slot] - head;
+            if (avail >= 32u || (fin && avail)) break;
+            if (sh.abort || ++spins > kQSpinMax) {           // never hang: flag the call and leave
+                if (lane == 0 && !sh.abort) { sh.abort = 1u; src.fail(); }
+                avail = 0;
+                break;
+            }
+            __nanosleep(64);
+        }
+        if (avail == 0) break;
+        __threadfence_block();
+        uint32_t n = min(avail, 32u);
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if ((uint32_t)lane < n) rec = q[(head + lane) & kQMask];
+        const unsigned marks = __ballot_sync(kFull, (uint32_t)lane < n && rec.y == kQMarker);
+        if (marks) n = (uint32_t)__ffs(marks) - 1u;
+        if (n) rowq_batch(ring, obase, gout, op, pad, rec, n, lane);
+        head += n;
+        bool quit = false;
+        if (marks) {
+            const int mk = __ffs(marks) - 1;
+            const uint32_t kind = __shfl_sync(kFull, rec.w, mk), arg = __shfl_sync(kFull, rec.x, mk);
+            head += 1u;
+            if (open) { ring.close(); open = false; }
+            if (kind == kQQuit) quit = true;
+            else {
+                QUnit u;
+                src.open(arg, u);
+                const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(u.out) & 31);
+                gout = u.out - a;                            // rows are aligned 32-byte sectors of the output
+                op = a;
+                pad = ring.open(u.in, u.clen);
+                open = true;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); sh.head[slot] = head; }
+        if (quit) break;
+    }
+    if (open) ring.close();                                  // (watchdog exit) nothing may stay in flight
+}
+
+template <bool SNAPPY, class Src>
+__device__ __forceinline__ void rowq_run(QShared& sh, const Src& src, uint32_t nunits, unsigned int* ticket) {
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x < kQSlots) { sh.tail[threadIdx.x] = 0; sh.head[threadIdx.x] = 0; sh.done[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) sh.abort = 0;
+    __syncthreads();
+    if (warp == 0) rowq_parse<SNAPPY>(sh, src, nunits, ticket, lane);
+    else rowq_copy(sh, src, warp - 1, lane);
+}
+
+}  // namespace llc

@@ -46,15 +46,16 @@ struct aocl_gpu_ctx_s {
     CallResult* d_res = nullptr;    // result block on the device
     CallResult* h_res = nullptr;    // pinned mirror
     int decode_blocks = 0;          // persistent grid size of decode_parts_kernel
-    int ws_blocks = 0;              // persistent grid size of decode_parts_ws_kernel
-    // Decoder organisation (AOCL_GPU_DECODER).  Measured on B200, 1 GiB frames (LZ4 text / Snappy log):
-    //   tile   (default) one 512-thread CTA per partition, thread per byte:      6.6 ms   / 5.4 ms  (first version: 11.2 / 8.5)
-    //   warp   one warp per partition: LZ4 TMA-ring pipelined decoder            14.2 ms  / 11.9 ms
-    //   ws     parser warp + lane-per-sequence copier warp per partition:        16-19 ms / 15.5 ms
-    //   bundle 32 lane-parsers + 16 copier warps per CTA:                        22 ms    / 18 ms
-    int decoder_mode = 4;
-    int pages_mode = 4;             // batched pages: tile decoder too since the thread-per-byte rewrite (262,144 x 64 KiB
-                                    // pages: LZ4 100 GB/s vs 66 GB/s warp-per-page, Snappy 155 vs 138); env overrides
+    // Decoder organisation (AOCL_GPU_DECODER = auto | rowq | tile | warp).  Measured on B200, 1 GiB frames
+    // (LZ4 text / Snappy log), ms per GiB:
+    //   rowq   lane parsers + thread-per-byte row copiers, 28 partitions in flight per SM  
+    //   tile   one 512-thread CTA per partition, data-parallel parse, pointer jumping:       6.45 / 5.05
+    //   warp   one warp per partition: LZ4 TMA-ring pipelined decoder                        14.2 / 11.9
+    // auto (default): the row decoder when a launch has at least rowq_min_units units (it needs several units
+    // per SM in flight), else the tile decoder.  Round 1 also measured a parser warp + lane-per-sequence copier
+    // (16-19 ms) and lane parsers + lane-per-sequence copiers against global memory (22 ms); both are gone.
+    int decoder_mode = 0;           // 0 auto, 1 warp, 4 tile, 5 rowq
+    uint32_t rowq_min_units = 0;    // AOCL_GPU_ROWQ_MIN_UNITS (default 5 x SMs)
     bool lz4_frameless = false;
     const uint32_t* in_flag = nullptr;   // one-shot input watermark for the next compress (aocl_gpu_set_input_watermark)
     bool batch_mode = false;        // last enqueue was a batch call (finish() returns -failures)
@@ -136,16 +137,18 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_parts_kernel, 128, 0);
     if (per_sm < 1) per_sm = 1;
     c->decode_blocks = per_sm * c->sm_count;
-    per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_parts_ws_kernel, 64, 0);
-    if (per_sm < 1) per_sm = 1;
-    c->ws_blocks = per_sm * c->sm_count;
+    c->rowq_min_units = 5u * (uint32_t)c->sm_count;
+    if (const char* e = getenv("AOCL_GPU_ROWQ_MIN_UNITS")) c->rowq_min_units = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("AOCL_GPU_DECODER"))
-        c->pages_mode = c->decoder_mode = strcmp(e, "ws") == 0 ? 2 : strcmp(e, "bundle") == 0 ? 3 : strcmp(e, "warp") == 0 ? 1 : 4;
+        c->decoder_mode = strcmp(e, "rowq") == 0 ? 5 : strcmp(e, "tile") == 0 ? 4 : strcmp(e, "warp") == 0 ? 1 : 0;
     cudaFuncSetAttribute(decode_parts_tile_kernel<TileLz4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileLz4>));
     cudaFuncSetAttribute(decode_parts_tile_kernel<TileSnappy, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileSnappy>));
     cudaFuncSetAttribute(decode_pages_tile_kernel<TileLz4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileLz4>));
     cudaFuncSetAttribute(decode_pages_tile_kernel<TileSnappy, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared<TileSnappy>));
+    cudaFuncSetAttribute(decode_parts_rowq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QShared));
+    cudaFuncSetAttribute(decode_parts_rowq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QShared));
+    cudaFuncSetAttribute(decode_pages_rowq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QShared));
+    cudaFuncSetAttribute(decode_pages_rowq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QShared));
     *out = c;
     return 0;
 }
@@ -255,24 +258,34 @@ extern "C" int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t c, int32_t cod
 // context's stream; aocl_gpu_finish() then returns the stream's total or the first error.
 static void launch_decode_range(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, void* d_out, PartDesc* parts,
                                 uint32_t first, uint32_t count, uint64_t out_origin) {
-    if (c->decoder_mode == 4) {
+    const uint8_t* in = (const uint8_t*)d_in;
+    uint8_t* out = (uint8_t*)d_out;
+    if (c->decoder_mode == 1) {
+        LLC_LAUNCH(decode_parts_kernel, c->decode_blocks, 128, 0, c->stream, codec, in, out, parts, c->d_res, first, count, out_origin);
+        return;
+    }
+    // The number of partitions is only known on the device: in auto mode both organisations are launched and the
+    // one whose regime it is not returns at once (decode_range_info).  A range of `count` partitions can never
+    // reach the row decoder's regime when count itself is below the threshold, so that launch is skipped.
+    const bool tile = c->decoder_mode != 5, rowq = c->decoder_mode != 4 && (c->decoder_mode == 5 || count >= c->rowq_min_units);
+    const uint32_t thr = c->decoder_mode == 5 ? 0u : c->rowq_min_units;
+    const uint32_t tile_max = rowq ? (thr ? thr - 1u : 0u) : 0xffffffffu;
+    if (tile && !(rowq && thr == 0)) {
         if (codec == AOCL_GPU_LZ4)
             LLC_LAUNCH((decode_parts_tile_kernel<TileLz4, false>), 2 * c->sm_count, kTThreads, sizeof(TileShared<TileLz4>), c->stream,
-                       (const uint8_t*)d_in, (uint8_t*)d_out, parts, c->d_res, first, count, out_origin);
+                       in, out, parts, c->d_res, first, count, out_origin, tile_max);
         else
             LLC_LAUNCH((decode_parts_tile_kernel<TileSnappy, true>), 2 * c->sm_count, kTThreads, sizeof(TileShared<TileSnappy>), c->stream,
-                       (const uint8_t*)d_in, (uint8_t*)d_out, parts, c->d_res, first, count, out_origin);
-    } else if (c->decoder_mode == 3) {
-        // the partition count is only known on the device here; size bundles for a 1 GiB-class frame
-        const uint32_t bundle = 28;
-        LLC_LAUNCH(decode_parts_bundle_kernel, c->sm_count, kBThreads, 0, c->stream, codec, (const uint8_t*)d_in,
-                   (uint8_t*)d_out, parts, c->d_res, first, count, out_origin, bundle);
-    } else if (c->decoder_mode == 1)
-        LLC_LAUNCH(decode_parts_kernel, c->decode_blocks, 128, 0, c->stream, codec, (const uint8_t*)d_in, (uint8_t*)d_out,
-                   parts, c->d_res, first, count, out_origin);
-    else
-        LLC_LAUNCH(decode_parts_ws_kernel, c->ws_blocks, 64, 0, c->stream, codec, (const uint8_t*)d_in, (uint8_t*)d_out,
-                   parts, c->d_res, first, count, out_origin);
+                       in, out, parts, c->d_res, first, count, out_origin, tile_max);
+    }
+    if (rowq) {
+        if (codec == AOCL_GPU_LZ4)
+            LLC_LAUNCH((decode_parts_rowq_kernel<false>), c->sm_count, kQThreads, sizeof(QShared), c->stream,
+                       in, out, parts, c->d_res, first, count, out_origin, thr);
+        else
+            LLC_LAUNCH((decode_parts_rowq_kernel<true>), c->sm_count, kQThreads, sizeof(QShared), c->stream,
+                       in, out, parts, c->d_res, first, count, out_origin, thr);
+    }
 }
 
 extern "C" int32_t aocl_gpu_decompress_open_async(aocl_gpu_ctx_t c, int32_t codec, const void* d_in, size_t n, size_t out_cap) {
@@ -463,8 +476,24 @@ extern "C" int32_t aocl_gpu_decompress_batch_async(aocl_gpu_ctx_t c, int32_t cod
         c->last_rc = -2; return -2;
     }
     if (count) {
-        const bool warp_decoder = c->pages_mode != 2;
-        if (c->pages_mode == 4) {
+        const bool want_rowq = c->decoder_mode == 5 || (c->decoder_mode == 0 && count >= c->rowq_min_units);
+        if (c->decoder_mode == 1) {
+            const uint64_t blocks = (count + 3) / 4;
+            const int grid = (int)(blocks < (uint64_t)c->decode_blocks * 4 ? blocks : (uint64_t)c->decode_blocks * 4);
+            LLC_LAUNCH(decode_pages_kernel, grid, 128, 0, c->stream, codec, (const uint8_t* const*)d_in_ptrs, d_in_sizes,
+                       (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status, (uint64_t)count, c->d_res);
+        } else if (want_rowq && count <= 0xffffffffull) {
+            const uint64_t ctas = (count + kQSlots - 1) / kQSlots;
+            const int grid = (int)(ctas < (uint64_t)c->sm_count ? ctas : (uint64_t)c->sm_count);
+            if (codec == AOCL_GPU_LZ4)
+                LLC_LAUNCH((decode_pages_rowq_kernel<false>), grid, kQThreads, sizeof(QShared), c->stream,
+                           (const uint8_t* const*)d_in_ptrs, d_in_sizes, (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status,
+                           (uint32_t)count, c->d_res);
+            else
+                LLC_LAUNCH((decode_pages_rowq_kernel<true>), grid, kQThreads, sizeof(QShared), c->stream,
+                           (const uint8_t* const*)d_in_ptrs, d_in_sizes, (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status,
+                           (uint32_t)count, c->d_res);
+        } else {
             const int grid = (int)(count < (uint64_t)c->sm_count * 2 ? count : (uint64_t)c->sm_count * 2);
             if (codec == AOCL_GPU_LZ4)
                 LLC_LAUNCH((decode_pages_tile_kernel<TileLz4, false>), grid, kTThreads, sizeof(TileShared<TileLz4>), c->stream,
@@ -474,15 +503,6 @@ extern "C" int32_t aocl_gpu_decompress_batch_async(aocl_gpu_ctx_t c, int32_t cod
                 LLC_LAUNCH((decode_pages_tile_kernel<TileSnappy, true>), grid, kTThreads, sizeof(TileShared<TileSnappy>), c->stream,
                            (const uint8_t* const*)d_in_ptrs, d_in_sizes, (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status,
                            (uint64_t)count, c->d_res);
-        } else if (warp_decoder) {
-            const uint64_t blocks = (count + 3) / 4;
-            const int grid = (int)(blocks < (uint64_t)c->decode_blocks * 4 ? blocks : (uint64_t)c->decode_blocks * 4);
-            LLC_LAUNCH(decode_pages_kernel, grid, 128, 0, c->stream, codec, (const uint8_t* const*)d_in_ptrs, d_in_sizes,
-                       (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status, (uint64_t)count, c->d_res);
-        } else {
-            const int grid = (int)(count < (uint64_t)c->ws_blocks * 2 ? count : (uint64_t)c->ws_blocks * 2);
-            LLC_LAUNCH(decode_pages_ws_kernel, grid, 64, 0, c->stream, codec, (const uint8_t* const*)d_in_ptrs, d_in_sizes,
-                       (uint8_t* const*)d_out_ptrs, d_out_caps, (long long*)d_status, (uint64_t)count, c->d_res);
         }
     }
     end_call(c);

@@ -7,9 +7,8 @@
 #include "snappy_encode_lean.cuh"
 #include "snappy_codec.cuh"
 #include "lz4_decode_ring.cuh"
-#include "decode_wspec.cuh"
-#include "decode_bundle.cuh"
 #include "decode_tile.cuh"
+#include "decode_rowq.cuh"
 
 namespace llc {
 
@@ -133,6 +132,28 @@ __global__ void __launch_bounds__(1024) rap_parse_kernel(int codec, const uint8_
     }
 }
 
+// The decode kernels of a partition range read the same three things from the result block: a sticky error
+// (an earlier kernel of the call failed), the partition count, and -- because the host does not know how many
+// partitions a device-resident stream has -- which decoder organisation serves this range: both organisations
+// are launched and the one whose regime it is not returns at once.  Thread 0 reads, everybody takes the broadcast
+// value, so a CTA never exits half way (another CTA of the same launch may raise res->error at any time).
+struct RangeInfo { uint32_t first, n; bool run; };
+__device__ __forceinline__ RangeInfo decode_range_info(const CallResult* res, uint32_t first, uint32_t count,
+                                                       uint32_t min_units, uint32_t max_units) {
+    __shared__ uint32_t s_info[2];
+    if (threadIdx.x == 0) {
+        const uint32_t T = (uint32_t)res->parts;
+        const uint32_t end = min(T, first + min(count, T));
+        const uint32_t n = end > first ? end - first : 0u;
+        s_info[0] = n;
+        s_info[1] = (res->error == 0 && n >= min_units && n <= max_units) ? 1u : 0u;
+    }
+    __syncthreads();
+    RangeInfo r;
+    r.first = first; r.n = s_info[0]; r.run = s_info[1] != 0;
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // Decompress step 2: persistent grid, one warp per partition, partitions handed out through an
 // atomic ticket so long partitions do not serialise a CTA.  Decodes partitions
@@ -143,11 +164,11 @@ __global__ void __launch_bounds__(128) decode_parts_kernel(int codec, const uint
                                                            uint32_t first, uint32_t count, uint64_t origin) {
     __shared__ RingStorage ring_mem[4];
     const int lane = lane_id();
+    const RangeInfo ri = decode_range_info(res, first, count, 0u, 0xffffffffu);
+    if (!ri.run) return;
     Ring ring;
     ring.init(&ring_mem[threadIdx.x >> 5], lane);
-    if (res->error) return;
-    const uint32_t T = (uint32_t)res->parts;
-    const uint32_t end = min(T, first + min(count, T));
+    const uint32_t end = first + ri.n;
     for (;;) {
         uint32_t i = 0;
         if (lane == 0) i = first + atomicAdd(&res->next, 1u);
@@ -166,123 +187,21 @@ __global__ void __launch_bounds__(128) decode_parts_kernel(int codec, const uint
     }
 }
 
-// Warp-specialised variant (decode_wspec.cuh): one CTA of two warps (parser + copier) per partition,
-// partitions handed out through the same atomic ticket.
-__global__ void __launch_bounds__(64, 24) decode_parts_ws_kernel(int codec, const uint8_t* __restrict__ in, uint8_t* out,
-                                                                 const PartDesc* __restrict__ parts, CallResult* res,
-                                                                 uint32_t first, uint32_t count, uint64_t origin) {
-    LLC_WS_SHARED(sh);
-    const int lane = lane_id();
-    Ring ring;
-    if (threadIdx.x < 32) ring.init(ws_ring_data(sh), sh.ring_bar, lane);
-    __syncthreads();
-    if (res->error) return;
-    const uint32_t T = (uint32_t)res->parts;
-    const uint32_t end = min(T, first + min(count, T));
-    for (;;) {
-        if (threadIdx.x == 0) sh.unit = first + atomicAdd(&res->next, 1u);
-        __syncthreads();
-        const uint32_t i = sh.unit;
-        __syncthreads();
-        if (i >= end) break;
-        const PartDesc d = parts[i];
-        if (d.in_len == 0) continue;
-        const int64_t got = ws_decode_unit(&sh, ring, codec, in + d.in_off, d.in_len, out + (d.out_off - origin), d.out_len,
-                                           (d.flags & kPartLast) != 0);
-        if (threadIdx.x == 0) {
-            if (got < 0 || ((d.flags & kPartExact) && (uint64_t)got != d.out_len)) atomicCAS(&res->error, 0, (int)i + 1);
-            else if (!(d.flags & kPartExact)) res->value = got;     // frame-less LZ4: size is whatever was produced
-        }
-    }
-}
-
-__global__ void __launch_bounds__(64, 24) decode_pages_ws_kernel(int codec, const uint8_t* const* __restrict__ in_ptrs,
-                                                                 const uint32_t* __restrict__ in_sizes, uint8_t* const* out_ptrs,
-                                                                 const uint32_t* __restrict__ out_caps, long long* status,
-                                                                 uint64_t count, CallResult* res) {
-    LLC_WS_SHARED(sh);
-    const int lane = lane_id();
-    Ring ring;
-    if (threadIdx.x < 32) ring.init(ws_ring_data(sh), sh.ring_bar, lane);
-    __syncthreads();
-    for (uint64_t i = blockIdx.x; i < count; i += gridDim.x) {
-        const uint8_t* in = in_ptrs[i];
-        const uint32_t n = in_sizes[i], cap = out_caps[i];
-        int64_t got;
-        if (codec == 0) got = ws_decode_unit(&sh, ring, 0, in, n, out_ptrs[i], cap, true);
-        else {
-            uint32_t total = 0;
-            const uint32_t vb = get_varint32(in, n, &total);
-            if (vb == 0 || total > cap) got = kErrCorrupt;
-            else got = ws_decode_unit(&sh, ring, 4, in + vb, n - vb, out_ptrs[i], total, true);
-        }
-        if (threadIdx.x == 0) {
-            status[i] = got;
-            if (got < 0) atomicAdd(&res->error, 1);
-        }
-        __syncthreads();
-    }
-}
-
-// Bundle variant (decode_bundle.cuh): one CTA = 32 lane-parsers + 16 copier warps; bundles of
-// `bundle` consecutive partitions are handed out through the atomic ticket.
-__global__ void __launch_bounds__(kBThreads, 1) decode_parts_bundle_kernel(int codec, const uint8_t* __restrict__ in, uint8_t* out,
-                                                                           const PartDesc* __restrict__ parts, CallResult* res,
-                                                                           uint32_t first, uint32_t count, uint64_t origin,
-                                                                           uint32_t bundle) {
-    __shared__ BShared sh;
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    if (res->error) return;
-    const uint32_t T = (uint32_t)res->parts;
-    const uint32_t end = min(T, first + min(count, T));
-    for (;;) {
-        if (threadIdx.x == 0) sh.bundle = atomicAdd(&res->next, 1u);
-        __syncthreads();
-        const uint64_t base_i = (uint64_t)first + (uint64_t)sh.bundle * bundle;
-        if (base_i >= end) break;
-        if (threadIdx.x < kBSlots) {
-            BSlot& sl = sh.slot[threadIdx.x];
-            const uint64_t i = base_i + threadIdx.x;
-            sl.flags = 0; sl.tail = 0; sl.head = 0; sl.done = 0; sl.result = 0;
-            if (threadIdx.x < bundle && i < end) {
-                const PartDesc d = parts[i];
-                if (d.in_len != 0) {
-                    sl.in = in + d.in_off; sl.out = out + (d.out_off - origin);
-                    sl.clen = d.in_len; sl.cap = d.out_len;
-                    sl.flags = kBUsed | ((d.flags & kPartLast) ? kBLast : 0u) | ((d.flags & kPartExact) ? kBExact : 0u) |
-                               (codec != 0 ? kBSnappy : 0u);
-                }
-            }
-        }
-        __syncthreads();
-        if (warp == 0) bundle_parse(&sh, lane);
-        else bundle_copy(&sh, warp - 1, lane);
-        __syncthreads();
-        if (threadIdx.x < kBSlots) {
-            const BSlot& sl = sh.slot[threadIdx.x];
-            if (sl.flags & kBUsed) {
-                const long long got = sl.result;
-                if (got < 0 || ((sl.flags & kBExact) && (uint64_t)got != sl.cap)) atomicCAS(&res->error, 0, (int)(base_i + threadIdx.x) + 1);
-                else if (!(sl.flags & kBExact)) res->value = got;       // frame-less LZ4: size is whatever was produced
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // Tile variant (decode_tile.cuh): one 512-thread CTA per partition, lane per sequence for the parse, thread
 // per byte for the copies, 32 KiB output window in shared memory; partitions handed out through the atomic ticket.
+// Serves ranges of fewer than `max_units + 1` partitions (too few units per SM for the row decoder).
 template <class Fmt, bool SNAPPY>
 __global__ void __launch_bounds__(kTThreads, 2) decode_parts_tile_kernel(const uint8_t* __restrict__ in, uint8_t* out,
                                                                         const PartDesc* __restrict__ parts, CallResult* res,
-                                                                        uint32_t first, uint32_t count, uint64_t origin) {
+                                                                        uint32_t first, uint32_t count, uint64_t origin,
+                                                                        uint32_t max_units) {
     extern __shared__ __align__(128) uint8_t tile_smem[];
     TileShared<Fmt>& sh = *reinterpret_cast<TileShared<Fmt>*>(tile_smem);
-    if (res->error) return;
+    const RangeInfo ri = decode_range_info(res, first, count, 0u, max_units);
+    if (!ri.run) return;
     tile_init(sh);
     uint32_t par = 0;
-    const uint32_t T = (uint32_t)res->parts;
-    const uint32_t end = min(T, first + min(count, T));
+    const uint32_t end = first + ri.n;
     for (;;) {
         if (threadIdx.x == 0) sh.unit = first + atomicAdd(&res->next, 1u);
         __syncthreads();
@@ -326,6 +245,34 @@ __global__ void __launch_bounds__(kTThreads, 2) decode_pages_tile_kernel(const u
         }
         __syncthreads();
     }
+}
+
+// Row variant (decode_rowq.cuh): one CTA per SM, 28 partitions in flight per CTA (one parser lane + one copier
+// warp each).  Serves ranges of at least `min_units` partitions.
+template <bool SNAPPY>
+__global__ void __launch_bounds__(kQThreads, 1) decode_parts_rowq_kernel(const uint8_t* __restrict__ in, uint8_t* out,
+                                                                        const PartDesc* __restrict__ parts, CallResult* res,
+                                                                        uint32_t first, uint32_t count, uint64_t origin,
+                                                                        uint32_t min_units) {
+    extern __shared__ __align__(128) uint8_t rowq_smem[];
+    QShared& sh = *reinterpret_cast<QShared*>(rowq_smem);
+    const RangeInfo ri = decode_range_info(res, first, count, min_units, 0xffffffffu);
+    if (!ri.run) return;
+    QPartsSource src;
+    src.in = in; src.out = out; src.parts = parts; src.res = res; src.first = first; src.origin = origin;
+    rowq_run<SNAPPY>(sh, src, ri.n, &res->next);
+}
+
+template <bool SNAPPY>
+__global__ void __launch_bounds__(kQThreads, 1) decode_pages_rowq_kernel(const uint8_t* const* __restrict__ in_ptrs,
+                                                                        const uint32_t* __restrict__ in_sizes, uint8_t* const* out_ptrs,
+                                                                        const uint32_t* __restrict__ out_caps, long long* status,
+                                                                        uint32_t count, CallResult* res) {
+    extern __shared__ __align__(128) uint8_t rowq_smem[];
+    QShared& sh = *reinterpret_cast<QShared*>(rowq_smem);
+    QPagesSource<SNAPPY> src;
+    src.in_ptrs = in_ptrs; src.in_sizes = in_sizes; src.out_ptrs = out_ptrs; src.out_caps = out_caps; src.status = status; src.res = res;
+    rowq_run<SNAPPY>(sh, src, count, &res->next);
 }
 
 // Range decode needs the byte count of the range rather than of the whole stream.

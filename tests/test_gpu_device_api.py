@@ -138,14 +138,15 @@ def test_batched_pages(torch_mod, ctx, oracle, codec):
     assert failed in (0, 1) and all(st3[i] == sizes[i] for i in range(24) if i != 3)
 
 
-@pytest.mark.parametrize("mode", ["ws", "bundle"])
-def test_alternative_decoders(mode):
-    """The other decoder organisations must produce the same bytes (run in a fresh process: the choice is
-    read once when the context is created)."""
+@pytest.mark.parametrize("mode", ["rowq", "tile", "warp"])
+def test_every_decoder_organisation(mode):
+    """The default picks the decoder by the number of units in a launch (row decoder for large frames, tile decoder
+    below); every organisation, forced for ALL sizes, must pass the whole parity / known-answer / hostile-stream
+    suite (run in a fresh process: the choice is read once when the context is created)."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, AOCL_GPU_DECODER=mode)
-    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu",
-                        os.path.join(root, "tests", "test_gpu_parity.py"), "-k", "decompress or round_trip"],
+    files = [os.path.join(root, "tests", f) for f in ("test_gpu_parity.py", "test_gpu_kat.py", "test_synth_streams.py")]
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu"] + files,
                        env=env, capture_output=True, text=True, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 

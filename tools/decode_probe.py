@@ -1,10 +1,11 @@
-"""Tile-decoder bring-up probe: decode oracle-compressed inputs of several generators/sizes with
-AOCL_GPU_DECODER=tile, compare with the input, print phase counters.  Run under gpurun."""
+"""Decoder bring-up probe: decode oracle-compressed inputs of several generators/sizes with the decoder
+AOCL_GPU_DECODER selects (auto | rowq | tile | warp), compare with the input, print the tile phase counters.
+Run under gpurun."""
 import ctypes as C, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "aocl-compression_b200", "python"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ.setdefault("AOCL_GPU_DECODER", "tile")
+
 import numpy as np, torch, llc_b200
 import kat, oracle_lib as ol
 from llc_b200 import gen
