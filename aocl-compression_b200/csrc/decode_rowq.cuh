@@ -45,14 +45,19 @@ constexpr uint32_t kORing = 4096, kORingMask = kORing - 1;   // output bytes kep
 constexpr uint32_t kQMarker = 0xffffffffu;                   // rec.y of a marker record: rec.w = kind, rec.x = argument
 constexpr uint32_t kQBegin = 1u, kQQuit = 2u;
 constexpr uint32_t kQCapMax = 0xfffe0000u;                  // positions + ring size must not wrap
-constexpr uint32_t kQSpinMax = 1u << 23;                     // copier watchdog (~1 s of polling)
+constexpr uint32_t kPChunkLog = 8, kPChunk = 1u << kPChunkLog;   // parser window: two 256-byte chunks per unit
+constexpr uint32_t kPWin = 2 * kPChunk, kPWinMask = kPWin - 1;
+constexpr uint32_t kPReach = 72;                             // a fast step reads stream bytes [ip, ip + kPReach)
+constexpr uint32_t kQSpinMax = 1u << 20;                     // copier watchdog (~1 s of sleeping polls)
 constexpr uint32_t kUnitBad = 0x100u;                        // QUnit.flags: the unit header itself is malformed
 
 struct QShared {
     alignas(128) uint8_t oring[kQSlots][kORing];
     alignas(128) uint8_t idata[kQSlots][kRingBytes];
+    alignas(128) uint8_t pwin[kQSlots][kPWin];               // parser lanes' own view of their streams (TMA fed)
     uint4 q[kQSlots * kQStride];
     alignas(8) uint64_t ibar[kQSlots][kStages];
+    alignas(8) uint64_t pbar[kQSlots][2];
     volatile uint32_t tail[kQSlots];                         // records published by the parser lane
     volatile uint32_t head[kQSlots];                         // records retired by the copier
     volatile uint32_t done[kQSlots];                         // the parser lane has published its last record
@@ -99,69 +104,141 @@ struct QPagesSource {
 };
 
 // ----------------------------------------------------------------------------------------- parsers
-// 8 bytes at p, any alignment, from the two aligned 8-byte words that hold them.
-__device__ __forceinline__ uint64_t ldg_win64(const uint8_t* p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint64_t* w = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
-    const unsigned sh = (unsigned)(a & 7) * 8;
-    const uint64_t lo = w[0], hi = w[1];
-    return sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
-}
-
-// Per-lane parser state (registers).  Positions are offsets from the unit's first byte.
+// Per-lane parser state (registers).  Positions are offsets from gbase, the 16-byte aligned address at or below
+// the unit's first byte (the unit starts at position `pad`).
+//
+// The lane reads its stream through a private two-chunk window in shared memory that it fills itself with the
+// TMA bulk-copy engine: 32 lanes that walk 32 different streams through L1 in lock step pay somebody's cache
+// miss in almost every iteration (measured: ~1 us per sequence); from shared memory an iteration costs one
+// 30-cycle load.  `lo` is the chunk that holds ip, `hi` the highest chunk known to have landed (lo or lo + 1);
+// chunk lo + 1 is always in flight or landed, and entering it frees the buffer of chunk lo for chunk lo + 2.
 struct QLane {
-    const uint8_t* in;
-    uint32_t ip, iend, op, cap;
+    const uint8_t* gbase;
+    uint32_t ip, iend, op, cap;        // iend: stream end (relative to gbase)
     uint32_t fast_i_ex, fast_o_ex;     // exclusive bounds of the region where no end rule can fire
-    uint64_t w;                        // the 8 stream bytes at ip (valid when wvalid)
-    bool wvalid, last, bad;
+    uint32_t pad;
+    uint32_t wbase;                    // shared-space address of the window
+    uint64_t* bar;                     // its two mbarriers
+    uint32_t lo, hi, pstate;           // pstate: bits 0-1 parity of the next phase per buffer, bits 2-3 load pending
+    bool last, bad;
 };
+
+__device__ __forceinline__ void qwin_wait(QLane& s, uint32_t b) {
+    if (s.pstate & (4u << b)) {
+        while (!mbar_try_wait(&s.bar[b], (s.pstate >> b) & 1u)) {}
+        s.pstate ^= (1u << b) | (4u << b);
+    }
+}
+__device__ __forceinline__ void qwin_issue(QLane& s, uint32_t c) {
+    const uint32_t base = c << kPChunkLog, b = c & 1u;
+    if (base >= s.iend) return;
+    const uint32_t left = s.iend - base;
+    const uint32_t bytes = left >= kPChunk ? kPChunk : ((left + 15u) & ~15u);
+    fence_proxy_async();                                     // my earlier reads of this buffer come first
+    mbar_expect_tx(&s.bar[b], bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s.wbase + b * kPChunk), "l"(s.gbase + base), "r"(bytes), "r"(smem_u32(&s.bar[b])) : "memory");
+    s.pstate |= 4u << b;
+}
+// (re)start the window at the chunk of s.ip
+__device__ __forceinline__ void qwin_open(QLane& s) {
+    qwin_wait(s, 0); qwin_wait(s, 1);
+    const uint32_t c = s.ip >> kPChunkLog;
+    s.lo = s.hi = c;
+    qwin_issue(s, c); qwin_issue(s, c + 1u);
+    qwin_wait(s, c & 1u);
+}
+// before a fast step at s.ip: every byte of [ip, ip + kPReach) has landed
+__device__ __forceinline__ void qwin_step(QLane& s) {
+    const uint32_t c = s.ip >> kPChunkLog, need = (s.ip + kPReach - 1u) >> kPChunkLog;
+    if (c != s.lo) { s.lo = c; qwin_issue(s, c + 1u); }      // chunk c - 1 is behind me: its buffer takes chunk c + 1
+    if (need != s.hi) { qwin_wait(s, need & 1u); s.hi = need; }
+}
+// 8 stream bytes at position p from the window (any alignment, wraps)
+__device__ __forceinline__ uint64_t qwin_ld64(const QLane& s, uint32_t p) {
+    const uint32_t a = p & ~3u;
+    const unsigned sh = (p & 3u) * 8u;
+    uint32_t w0, w1, w2;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(s.wbase + (a & kPWinMask)));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(s.wbase + ((a + 4u) & kPWinMask)));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(s.wbase + ((a + 8u) & kPWinMask)));
+    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+}
+__device__ __forceinline__ uint32_t qwin_ld32(const QLane& s, uint32_t p) {
+    const uint32_t a = p & ~3u;
+    uint32_t w0, w1;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(s.wbase + (a & kPWinMask)));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(s.wbase + ((a + 4u) & kPWinMask)));
+    return __funnelshift_r(w0, w1, (p & 3u) * 8u);
+}
 
 __device__ __forceinline__ void qpush(uint4* q, uint32_t& tail, uint32_t lp, uint32_t ll, uint32_t off, uint32_t ml) {
     q[tail & kQMask] = make_uint4(lp, ll, off, ml);
     tail++;
 }
 
-// One LZ4 sequence for this lane.  Returns false when the unit is finished (ok or bad).
-__device__ __forceinline__ bool qlane_step_lz4(QLane& s, uint4* q, uint32_t& tail) {
-    const uint8_t* in = s.in;
+// FAST STEP, LZ4.  Precondition: ip < fast_i_ex and op < fast_o_ex -- at least 319 stream bytes and 559 output
+// bytes ahead, so a sequence with at most one length byte each (ll <= 269, ml <= 273) cannot trigger an
+// end-of-block rule -- and qwin_step() has been called.  Straight-line code.  Returns 0: consumed, 1: not
+// consumed (a 255 length byte or a literal run too long for the window: take the general step), 2: corrupt.
+// Record positions are relative to the unit's first byte.
+__device__ __forceinline__ int qlane_fast_lz4(QLane& s, uint4* q, uint32_t& tail) {
     const uint32_t ip = s.ip;
-    if (ip >= s.iend) { s.bad = true; return false; }
-    if ((ip < s.fast_i_ex) & (s.op < s.fast_o_ex)) {
-        // at least 319 stream bytes and 559 output bytes ahead: a sequence with at most one length byte each
-        // (ll <= 269, ml <= 273) cannot trigger an end-of-block rule and all its reads stay inside the stream
-        const uint64_t w = s.wvalid ? s.w : ldg_win64(in + ip);
-        const uint32_t w0 = (uint32_t)w;
-        const uint32_t tok = w0 & 0xffu, e1 = (w0 >> 8) & 0xffu;
-        const uint32_t nibL = tok >> 4, nibM = tok & 15u;
-        const bool extL = nibL == 15u, extM = nibM == 15u;
-        const uint32_t ll = nibL + (extL ? e1 : 0u);
-        const uint32_t hdr = 1u + (extL ? 1u : 0u);
-        const uint32_t rel = hdr + ll;                      // the offset field, relative to ip
-        uint32_t t;                                         // offset (2 bytes) and the byte after it
-        if (rel <= 5u) t = (uint32_t)(w >> (8u * rel));
-        else t = ld_u32(in + ip + rel);
-        const uint32_t off = t & 0xffffu, e2 = (t >> 16) & 0xffu;
-        if (!((extL & (e1 == 255u)) | (extM & (e2 == 255u)))) {
-            const uint32_t ipn = ip + rel + 2u + (extM ? 1u : 0u);
-            s.wvalid = ipn < s.fast_i_ex;
-            if (s.wvalid) s.w = ldg_win64(in + ipn);        // next window: in flight during the checks below
-            const uint32_t ml = nibM + 4u + (extM ? e2 : 0u);
-            const uint32_t op2 = s.op + ll;
-            if ((off - 1u) >= op2) { s.bad = true; return false; }       // lz4.c:4196-4197
-            qpush(q, tail, ip + hdr, ll, off, ml);
-            s.op = op2 + ml;
-            if ((ipn >> 7) != (ip >> 7)) prefetch_l1(in + ((ipn >> 7) + 2u) * 128u);
-            s.ip = ipn;
-            return true;
-        }
-    }
-    s.wvalid = false;
-    // general case: length runs, block tail, tiny units -- every check of the reference
+    const uint64_t w = qwin_ld64(s, ip);
+    const uint32_t w0 = (uint32_t)w;
+    const uint32_t tok = w0 & 0xffu, e1 = (w0 >> 8) & 0xffu;
+    const uint32_t nibL = tok >> 4, nibM = tok & 15u;
+    const bool extL = nibL == 15u, extM = nibM == 15u;
+    const uint32_t ll = nibL + (extL ? e1 : 0u);
+    const uint32_t hdr = 1u + (extL ? 1u : 0u);
+    const uint32_t rel = hdr + ll;                          // the offset field, relative to ip
+    if (rel > kPReach - 4u) return 1;
+    uint32_t t = (uint32_t)(w >> (8u * (rel & 7u)));        // offset (2 bytes) and the byte after it
+    if (rel > 5u) t = qwin_ld32(s, ip + rel);
+    const uint32_t off = t & 0xffffu, e2 = (t >> 16) & 0xffu;
+    const uint32_t ml = nibM + 4u + (extM ? e2 : 0u);
+    const uint32_t op2 = s.op + ll;
+    const bool special = (extL & (e1 == 255u)) | (extM & (e2 == 255u));
+    const bool badoff = (off - 1u) >= op2;                  // lz4.c:4196-4197
+    if (special | badoff) return special ? 1 : 2;
+    qpush(q, tail, ip + hdr - s.pad, ll, off, ml);
+    s.op = op2 + ml;
+    s.ip = ip + rel + 2u + (extM ? 1u : 0u);
+    return 0;
+}
+
+// FAST STEP, Snappy.  Precondition: ip < fast_i_ex (319 stream bytes ahead), qwin_step() called.  Returns as
+// qlane_fast_lz4 (1: a 4-byte-offset copy or a literal with length bytes: take the general step).
+__device__ __forceinline__ int qlane_fast_snappy(QLane& s, uint4* q, uint32_t& tail) {
+    const uint32_t ip = s.ip, expect = s.cap;
+    const uint32_t w0 = qwin_ld32(s, ip);
+    const uint32_t tag = w0 & 0xffu, b1 = (w0 >> 8) & 0xffu, b2 = (w0 >> 16) & 0xffu;
+    const uint32_t kind = tag & 3u, hi = tag >> 2;
+    const bool is_lit = kind == 0u;
+    const uint32_t lit_len = hi + 1u;
+    const uint32_t cp_len = (kind == 1u) ? 4u + (hi & 7u) : 1u + hi;
+    const uint32_t cp_off = (kind == 1u) ? (((tag >> 5) << 8) | b1) : (b1 | (b2 << 8));
+    const uint32_t len = is_lit ? lit_len : cp_len;
+    const bool special = (kind == 3u) | (is_lit & (hi >= 60u - 0u)) | (is_lit & (lit_len > kPReach - 4u));
+    const bool badel = (len > expect - s.op) | (!is_lit & ((cp_off - 1u) >= s.op));   // snappy.cc:2185-2199
+    if (special | badel) return special ? 1 : 2;
+    qpush(q, tail, ip + 1u - s.pad, is_lit ? lit_len : 0u, is_lit ? 0u : cp_off, is_lit ? 0u : cp_len);
+    s.op += len;
+    s.ip = ip + (is_lit ? 1u + lit_len : (kind == 1u ? 2u : 3u));
+    return 0;
+}
+
+// One LZ4 sequence through the general code (bytes straight from global memory): length runs, block tail, tiny
+// units -- every check of the reference.  Returns false when the unit is finished (ok or bad).  Positions in the
+// lane state are relative to gbase; the arithmetic below is relative to the unit's first byte.
+__device__ __noinline__ bool qlane_step_lz4(QLane& s, uint4* q, uint32_t& tail) {
+    const uint8_t* in = s.gbase + s.pad;
+    const uint32_t ip = s.ip - s.pad;
+    const uint32_t iend = s.iend - s.pad, cap = s.cap;
+    if (ip >= iend) { s.bad = true; return false; }
     const uint32_t tok = in[ip];
     const uint32_t nibL = tok >> 4, nibM = tok & 15u;
     const bool last = s.last;
-    const uint32_t iend = s.iend, cap = s.cap;
     uint32_t p = ip + 1, ll = nibL;
     if (ll == 15u) {
         uint32_t b;
@@ -175,7 +252,7 @@ __device__ __forceinline__ bool qlane_step_lz4(QLane& s, uint4* q, uint32_t& tai
     const uint32_t qq = p + ll;
     if ((closing && (last || s.op == cap)) || qq == iend) {
         if (ll) qpush(q, tail, lit_pos, ll, 0, 0);
-        s.ip = qq;
+        s.ip = qq + s.pad;
         return false;
     }
     if (qq + 2 > iend) { s.bad = true; return false; }
@@ -191,44 +268,22 @@ __device__ __forceinline__ bool qlane_step_lz4(QLane& s, uint4* q, uint32_t& tai
     if (last && (uint64_t)s.op + ml + 5 > cap) { s.bad = true; return false; }       // lz4.c:4262-4264
     qpush(q, tail, lit_pos, ll, off, ml);
     s.op += ml;
-    s.ip = p;
-    prefetch_l1(in + ((p >> 7) + 1u) * 128u);
+    s.ip = p + s.pad;
     if (!last && (s.op == cap || p >= iend)) return false;                           // lz4.c:4285-4288
     return true;
 }
 
-// One Snappy element for this lane (cap is the exact size the stream must produce).
-__device__ __forceinline__ bool qlane_step_snappy(QLane& s, uint4* q, uint32_t& tail) {
-    const uint8_t* in = s.in;
-    const uint32_t ip = s.ip, iend = s.iend, expect = s.cap;
+// One Snappy element through the general code (cap is the exact size the stream must produce).
+__device__ __noinline__ bool qlane_step_snappy(QLane& s, uint4* q, uint32_t& tail) {
+    const uint8_t* in = s.gbase + s.pad;
+    const uint32_t ip = s.ip - s.pad, iend = s.iend - s.pad, expect = s.cap;
     if (ip >= iend) return false;
-    if (ip < s.fast_i_ex) {
-        const uint64_t w = s.wvalid ? s.w : ldg_win64(in + ip);
-        const uint32_t w0 = (uint32_t)w;
-        const uint32_t tag = w0 & 0xffu, b1 = (w0 >> 8) & 0xffu, b2 = (w0 >> 16) & 0xffu;
-        const uint32_t kind = tag & 3u, hi = tag >> 2;
-        if (kind != 3u && !(kind == 0u && hi >= 60u)) {
-            const bool is_lit = kind == 0u;
-            const uint32_t lit_len = hi + 1u;
-            const uint32_t ipn = ip + (is_lit ? 1u + lit_len : (kind == 1u ? 2u : 3u));
-            s.wvalid = ipn < s.fast_i_ex;
-            if (s.wvalid) s.w = ldg_win64(in + ipn);
-            const uint32_t cp_len = (kind == 1u) ? 4u + (hi & 7u) : 1u + hi;
-            const uint32_t cp_off = (kind == 1u) ? (((tag >> 5) << 8) | b1) : (b1 | (b2 << 8));
-            const uint32_t len = is_lit ? lit_len : cp_len;
-            if (len > expect - s.op || (!is_lit && (cp_off - 1u) >= s.op)) { s.bad = true; return false; }   // snappy.cc:2185-2199
-            qpush(q, tail, ip + 1u, is_lit ? lit_len : 0u, is_lit ? 0u : cp_off, is_lit ? 0u : cp_len);
-            s.op += len;
-            if ((ipn >> 7) != (ip >> 7)) prefetch_l1(in + ((ipn >> 7) + 2u) * 128u);
-            s.ip = ipn;
-            return true;
-        }
-    }
-    s.wvalid = false;
     const uint32_t tag = in[ip];
     const uint32_t kind = tag & 3u, hi = tag >> 2;
+    uint32_t len, off = 0, nip;
     if (kind == 0u) {                                   // literal, snappy.cc:1492-1527
-        uint32_t len = hi + 1u, p = ip + 1u;
+        uint32_t p = ip + 1u;
+        len = hi + 1u;
         if (len > 60u) {
             const uint32_t nb = len - 60u;
             if (p + nb > iend) { s.bad = true; return false; }
@@ -239,26 +294,27 @@ __device__ __forceinline__ bool qlane_step_snappy(QLane& s, uint4* q, uint32_t& 
         }
         if (len > iend - p || len > expect - s.op) { s.bad = true; return false; }
         qpush(q, tail, p, len, 0, 0);
-        s.op += len; s.ip = p + len;
-        prefetch_l1(in + ((s.ip >> 7) + 1u) * 128u);
-        return true;
+        nip = p + len;
+    } else {                                            // char_table, snappy-internal.h:406-439
+        uint32_t adv;
+        if (kind == 1u) {
+            if (ip + 2 > iend) { s.bad = true; return false; }
+            len = 4u + (hi & 7u); off = ((tag >> 5) << 8) | in[ip + 1]; adv = 2;
+        } else if (kind == 2u) {
+            if (ip + 3 > iend) { s.bad = true; return false; }
+            len = 1u + hi; off = (uint32_t)in[ip + 1] | ((uint32_t)in[ip + 2] << 8); adv = 3;
+        } else {
+            if (ip + 5 > iend) { s.bad = true; return false; }
+            len = 1u + hi;
+            off = (uint32_t)in[ip + 1] | ((uint32_t)in[ip + 2] << 8) | ((uint32_t)in[ip + 3] << 16) | ((uint32_t)in[ip + 4] << 24);
+            adv = 5;
+        }
+        if (off == 0 || off > s.op || len > expect - s.op) { s.bad = true; return false; }   // snappy.cc:2185-2199
+        qpush(q, tail, ip + 1u, 0, off, len);
+        nip = ip + adv;
     }
-    uint32_t len, off, adv;                             // char_table, snappy-internal.h:406-439
-    if (kind == 1u) {
-        if (ip + 2 > iend) { s.bad = true; return false; }
-        len = 4u + (hi & 7u); off = ((tag >> 5) << 8) | in[ip + 1]; adv = 2;
-    } else if (kind == 2u) {
-        if (ip + 3 > iend) { s.bad = true; return false; }
-        len = 1u + hi; off = (uint32_t)in[ip + 1] | ((uint32_t)in[ip + 2] << 8); adv = 3;
-    } else {
-        if (ip + 5 > iend) { s.bad = true; return false; }
-        len = 1u + hi;
-        off = (uint32_t)in[ip + 1] | ((uint32_t)in[ip + 2] << 8) | ((uint32_t)in[ip + 3] << 16) | ((uint32_t)in[ip + 4] << 24);
-        adv = 5;
-    }
-    if (off == 0 || off > s.op || len > expect - s.op) { s.bad = true; return false; }   // snappy.cc:2185-2199
-    qpush(q, tail, ip + 1u, 0, off, len);
-    s.op += len; s.ip = ip + adv;
+    s.op += len;
+    s.ip = nip + s.pad;
     return true;
 }
 
@@ -267,19 +323,39 @@ __device__ __forceinline__ bool qlane_step_snappy(QLane& s, uint4* q, uint32_t& 
 // with fewer units than slots spreads over all SMs), later ones come from the atomic ticket.
 template <bool SNAPPY, class Src>
 __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, unsigned int* ticket, int lane) {
-    uint4* const q = sh.q + (lane < kQSlots ? lane : 0) * kQStride;
+    const int slot = lane < kQSlots ? lane : 0;
+    uint4* const q = sh.q + slot * kQStride;
     QLane s;
     QUnit u;
-    s.in = nullptr; s.ip = s.iend = s.op = s.cap = s.fast_i_ex = s.fast_o_ex = 0; s.w = 0;
-    s.wvalid = false; s.last = false; s.bad = false;
+    s.gbase = nullptr; s.ip = s.iend = s.op = s.cap = s.fast_i_ex = s.fast_o_ex = s.pad = 0;
+    s.wbase = smem_u32(sh.pwin[slot]); s.bar = sh.pbar[slot];
+    s.lo = s.hi = 0; s.pstate = 0;
+    s.last = false; s.bad = false;
     u.in = nullptr; u.out = nullptr; u.clen = u.cap = u.flags = 0;
     uint32_t tail = 0, published = 0, head_c = 0, cur = 0;
     bool active = false, alive = lane < kQSlots, first_fetch = true;
     while (__any_sync(kFull, alive)) {
         if (sh.abort) break;
+        bool moved = false;
+        // ---- fast steps: up to 8 sequences per lane back to back (the bookkeeping below runs once per pass)
+        bool slow = !active;                                 // this lane needs the general code
+#pragma unroll 1
+        for (int it = 0; it < 8; it++) {
+            const bool can = active && !slow && (tail - head_c < kQCap) && s.ip < s.fast_i_ex && (SNAPPY || s.op < s.fast_o_ex);
+            if (!__any_sync(kFull, can)) break;
+            if (can) {
+                qwin_step(s);
+                const int r = SNAPPY ? qlane_fast_snappy(s, q, tail) : qlane_fast_lz4(s, q, tail);
+                if (r) { slow = true; if (r == 2) s.bad = true; }
+                moved = true;
+            }
+        }
         if (alive) {
             if (tail - head_c >= kQCap) head_c = sh.head[lane];
-            if (tail - head_c < kQCap) {
+            const bool room = tail - head_c < kQCap;
+            if (active && !slow && room && !(s.ip < s.fast_i_ex && (SNAPPY || s.op < s.fast_o_ex))) slow = true;   // left the fast region
+            if (room && slow) {
+                moved = true;
                 if (!active) {
                     uint32_t i;
                     if (first_fetch) { i = (uint32_t)lane * gridDim.x + blockIdx.x; first_fetch = false; }
@@ -289,20 +365,22 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
                         alive = false;
                     } else if (src.open(i, u)) {
                         cur = i;
-                        s.in = u.in; s.iend = u.clen; s.cap = min(u.cap, kQCapMax);
-                        s.ip = 0; s.op = 0; s.bad = false; s.wvalid = false;
+                        s.pad = (uint32_t)(reinterpret_cast<uintptr_t>(u.in) & 15);
+                        s.gbase = u.in - s.pad;
+                        s.iend = u.clen + s.pad; s.cap = min(u.cap, kQCapMax);
+                        s.ip = s.pad; s.op = 0; s.bad = false;
                         s.last = (u.flags & kPartLast) != 0;
-                        const bool any_fast = s.iend >= 320u && (SNAPPY || s.cap >= 560u);
+                        const bool any_fast = u.clen >= 320u && (SNAPPY || s.cap >= 560u);
                         s.fast_i_ex = any_fast ? s.iend - 319u : 0u;
                         s.fast_o_ex = (any_fast && !SNAPPY) ? s.cap - 559u : 0u;
                         bool run = true;
                         if (u.flags & kUnitBad) { s.bad = true; run = false; }
                         else if (!SNAPPY) {
-                            if (s.iend == 0) { s.bad = true; run = false; }
-                            else if (s.cap == 0) { s.bad = !(s.iend == 1 && s.in[0] == 0); run = false; }   // lz4.c:3854-3858
+                            if (u.clen == 0) { s.bad = true; run = false; }
+                            else if (s.cap == 0) { s.bad = !(u.clen == 1 && u.in[0] == 0); run = false; }   // lz4.c:3854-3858
                         }
                         if (run) {
-                            prefetch_l1(s.in + 128); prefetch_l1(s.in + 256);
+                            if (any_fast) qwin_open(s);
                             qpush(q, tail, i, kQMarker, 0, kQBegin);
                             active = true;
                         } else {
@@ -310,12 +388,15 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
                         }
                     }
                 } else {
-                    const bool more = SNAPPY ? qlane_step_snappy(s, q, tail) : qlane_step_lz4(s, q, tail);
+                    const bool more = !s.bad && (SNAPPY ? qlane_step_snappy(s, q, tail) : qlane_step_lz4(s, q, tail));
                     if (!more) {
                         long long r = s.bad ? kErrCorrupt : (long long)s.op;
                         if (!s.bad && SNAPPY && s.op != s.cap) r = kErrCorrupt;             // snappy.cc:1715
                         src.report(cur, r, u);
                         active = false;
+                    } else if (s.ip < s.fast_i_ex &&
+                               !((s.ip >> kPChunkLog) == s.lo && ((s.ip + kPReach - 1u) >> kPChunkLog) <= s.hi)) {
+                        qwin_open(s);                       // back to the fast steps, beyond what the window holds
                     }
                 }
             }
@@ -326,75 +407,104 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
                 if (!alive) { __threadfence_block(); sh.done[lane] = 1u; }
             }
         }
+        if (!__any_sync(kFull, moved)) __nanosleep(200);    // every queue is full: the copiers are the bottleneck
     }
+    qwin_wait(s, 0); qwin_wait(s, 1);                       // nothing may stay in flight
 }
 
 // ----------------------------------------------------------------------------------------- copiers
+// Per-batch constants of a copier (uniform across the warp unless noted).
+struct QBatch {
+    uint32_t op, total;          // output span of the batch: [op, op + total)
+    uint32_t sbase, obase;       // shared-space addresses of the input ring and of the output ring
+    const uint8_t* gin;          // input-ring base in global memory (positions are relative to it)
+    uint8_t* gout;               // 32-byte aligned output base (positions are relative to it)
+    uint32_t D, M, L, O;         // per lane = per record: first byte, first match byte, literal position - first byte, offset
+    uint32_t lemask;             // per lane: bits 1 .. lane
+};
+
+// One 32-byte row [x0, x0 + 32), lane per byte.  FULL: every byte of the row belongs to the batch.
+template <bool USE_RING, bool FULL>
+__device__ __forceinline__ void rowq_row(const QBatch& B, uint32_t x0, int lane) {
+    // which record covers byte x: the records that start at or before x0, plus the starts inside the row up to x
+    const uint32_t rel = B.D - x0;
+    uint32_t bit;
+    asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(rel));        // 0 when rel >= 32: PTX clamps the shift amount
+    const uint32_t bits = __reduce_or_sync(kFull, bit);
+    const uint32_t cnt0 = (uint32_t)__popc(__ballot_sync(kFull, B.D <= x0));
+    const uint32_t k = cnt0 - 1u + (uint32_t)__popc(bits & B.lemask);
+    const uint32_t m = __shfl_sync(kFull, B.M, (int)k), l = __shfl_sync(kFull, B.L, (int)k), o = __shfl_sync(kFull, B.O, (int)k);
+    const uint32_t x = x0 + (uint32_t)lane;
+    const bool live = FULL ? true : (x - B.op) < B.total;
+    const bool is_lit = x < m;
+    const bool mat = live && !is_lit;
+    // source x - o: inside this row (not written yet) / in the output ring / older than the ring (read back from L2)
+    const bool dep = FULL ? (mat && o <= (uint32_t)lane) : (mat && (x - o) >= max(x0, B.op));
+    const bool far = mat && o > (uint32_t)lane + (kORing - 32u);
+    uint32_t v = 0;
+    if (live && is_lit) v = USE_RING ? lds_u8(B.sbase + ((x + l) & kRingMask)) : (uint32_t)B.gin[x + l];
+    if (mat && !dep && !far) v = lds_u8(B.obase + ((x - o) & kORingMask));
+    if (__any_sync(kFull, far)) { if (far) v = __ldcg(B.gout + (x - o)); }
+    if (__any_sync(kFull, dep)) {
+        // pointer doubling over the lanes of the row: a byte whose source lane is still unknown adopts that
+        // lane's source; every round at least halves the chains (<= 5 rounds)
+        uint32_t j = (uint32_t)lane - o;
+        bool need = dep;
+        do {
+            const uint32_t vj = __shfl_sync(kFull, v, (int)j);
+            const uint32_t jj = __shfl_sync(kFull, j, (int)j);
+            const bool nj = __shfl_sync(kFull, need ? 1 : 0, (int)j) != 0;
+            if (need) { if (!nj) { v = vj; need = false; } else j = jj; }
+        } while (__any_sync(kFull, need));
+    }
+    if (live) {
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(B.obase + (x & kORingMask)), "r"(v) : "memory");
+        B.gout[x] = (uint8_t)v;
+    }
+    __syncwarp();
+}
+
+template <bool USE_RING>
+__device__ __forceinline__ void rowq_rows(const QBatch& B, int lane) {
+    const uint32_t op_end = B.op + B.total;
+    uint32_t x0 = B.op & ~31u;
+    if (x0 != B.op) { rowq_row<USE_RING, false>(B, x0, lane); x0 += 32u; }         // the batch starts inside a row
+    for (; x0 + 32u <= op_end; x0 += 32u) rowq_row<USE_RING, true>(B, x0, lane);
+    if (x0 < op_end) rowq_row<USE_RING, false>(B, x0, lane);                       // ... and ends inside one
+}
+
 // Executes the n (1..32) records held lane-per-record in `rec`; lanes >= n hold nothing.
 __device__ __forceinline__ void rowq_batch(Ring& ring, uint32_t obase, uint8_t* gout, uint32_t& op_io, uint32_t pad,
                                            const uint4 rec, uint32_t n, int lane) {
-    const uint32_t op = op_io;
+    QBatch B;
+    B.op = op_io;
     const bool valid = (uint32_t)lane < n;
     const uint32_t ll = valid ? rec.y : 0u, ml = valid ? rec.w : 0u;
     const uint32_t len = ll + ml;
     const uint32_t incl = warp_incl_sum(len, lane);
-    const uint32_t total = __shfl_sync(kFull, incl, 31);
-    const uint32_t d = op + incl - len;                      // first output byte of my record
-    const uint32_t D = valid ? d : 0xffffffffu;
-    const uint32_t M = d + ll;                               // first match byte of my record
+    B.total = __shfl_sync(kFull, incl, 31);
+    const uint32_t d = B.op + incl - len;                    // first output byte of my record
+    B.D = valid ? d : 0xffffffffu;
+    B.M = d + ll;
     const uint32_t lpos = rec.x + pad;                       // literals of my record in ring coordinates
-    const uint32_t L = lpos - d;                             // literal byte x of my record sits at ring position x + L
-    const uint32_t O = rec.z;
-    const uint32_t op_end = op + total;
+    B.L = lpos - d;                                          // literal byte x of my record sits at ring position x + L
+    B.O = rec.z;
+    B.lemask = ((2u << lane) - 1u) & ~1u;
+    B.obase = obase; B.gout = gout;
     // literal window of the batch (positions grow with the lane): the TMA ring when it fits, else global loads
     const uint32_t lit_lo = __shfl_sync(kFull, lpos, 0);
     const uint32_t lit_hi = __shfl_sync(kFull, lpos + ll, (int)n - 1);
     const bool use_ring = lit_hi <= (lit_lo & ~(kChunk - 1u)) + kRingBytes;
-    if (use_ring) { ring.advance(lit_lo, lane); ring.ensure(lit_hi); }
-    const uint32_t sbase = smem_u32(ring.sm);
-    const uint8_t* const gin = ring.gbase;
-    const uint32_t lemask = (2u << lane) - 1u;               // bits 0 .. lane
-    for (uint32_t x0 = op & ~31u; x0 < op_end; x0 += 32u) {
-        const uint32_t x = x0 + (uint32_t)lane;
-        const bool live = (x - op) < total;
-        // which record covers byte x: records that start at or before x0, plus the starts inside the row up to x
-        const uint32_t rel = D - x0;
-        const uint32_t bits = __reduce_or_sync(kFull, rel < 32u ? (1u << rel) : 0u);
-        const uint32_t cnt0 = (uint32_t)__popc(__ballot_sync(kFull, D <= x0));
-        const uint32_t k = cnt0 - 1u + (uint32_t)__popc(bits & ~1u & lemask);
-        const uint32_t m = __shfl_sync(kFull, M, (int)k), l = __shfl_sync(kFull, L, (int)k), o = __shfl_sync(kFull, O, (int)k);
-        const bool is_lit = x < m;
-        const uint32_t src = x - o;
-        const bool mat = live && !is_lit;
-        const uint32_t rowlo = max(x0, op);
-        const bool dep = mat && src >= rowlo;                // source inside this row: not written yet
-        const bool far = mat && (src + kORing < x0 + 32u);   // source has left the output ring: read back from L2
-        uint32_t v = 0;
-        if (live && is_lit) {
-            if (use_ring) v = lds_u8(sbase + ((x + l) & kRingMask));
-            else v = gin[x + l];
-        }
-        if (mat && !dep && !far) v = lds_u8(obase + (src & kORingMask));
-        if (__any_sync(kFull, far)) { if (far) v = __ldcg(gout + src); }
-        if (__any_sync(kFull, dep)) {
-            // pointer doubling over the lanes of the row: a byte whose source lane is still unknown
-            // adopts that lane's source; every round at least halves the chains (<= 5 rounds)
-            uint32_t j = src - x0;
-            bool need = dep;
-            do {
-                const uint32_t vj = __shfl_sync(kFull, v, (int)j);
-                const uint32_t jj = __shfl_sync(kFull, j, (int)j);
-                const bool nj = __shfl_sync(kFull, need ? 1 : 0, (int)j) != 0;
-                if (need) { if (!nj) { v = vj; need = false; } else j = jj; }
-            } while (__any_sync(kFull, need));
-        }
-        if (live) {
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(obase + (x & kORingMask)), "r"(v) : "memory");
-            gout[x] = (uint8_t)v;
-        }
-        __syncwarp();
+    B.sbase = smem_u32(ring.sm);
+    B.gin = ring.gbase;
+    if (use_ring) {
+        ring.advance(lit_lo, lane);
+        ring.ensure(lit_hi);
+        rowq_rows<true>(B, lane);
+    } else {
+        rowq_rows<false>(B, lane);
     }
-    op_io = op_end;
+    op_io = B.op + B.total;
 }
 
 // A copier warp: consumes the queue of its slot until the parser's QUIT marker.
@@ -408,18 +518,20 @@ __device__ inline void rowq_copy(QShared& sh, const Src& src, int slot, int lane
     uint8_t* gout = nullptr;
     bool open = false;
     for (;;) {
-        uint32_t avail, spins = 0;
+        // wait for a full batch (or for whatever is left once the parser lane is done); sleeping, not spinning:
+        // a polling copier takes issue slots from the parser warp it is waiting for
+        uint32_t avail, spins = 0, ns = 64;
         for (;;) {
-            const uint32_t fin = sh.done[slot];
-            __threadfence_block();
             avail = sh.tail[slot] - head;
-            if (avail >= 32u || (fin && avail)) break;
+            if (avail >= 32u) break;
+            if (sh.done[slot]) { __threadfence_block(); avail = sh.tail[slot] - head; if (avail) break; }
             if (sh.abort || ++spins > kQSpinMax) {           // never hang: flag the call and leave
                 if (lane == 0 && !sh.abort) { sh.abort = 1u; src.fail(); }
                 avail = 0;
                 break;
             }
-            __nanosleep(64);
+            __nanosleep(ns);
+            if (ns < 1024u) ns <<= 1;
         }
         if (avail == 0) break;
         __threadfence_block();
@@ -459,6 +571,10 @@ __device__ __forceinline__ void rowq_run(QShared& sh, const Src& src, uint32_t n
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     if (threadIdx.x < kQSlots) { sh.tail[threadIdx.x] = 0; sh.head[threadIdx.x] = 0; sh.done[threadIdx.x] = 0; }
     if (threadIdx.x == 0) sh.abort = 0;
+    if (threadIdx.x < kQSlots) {                             // parser windows: one mbarrier per buffer
+        mbar_init(&sh.pbar[threadIdx.x][0], 1); mbar_init(&sh.pbar[threadIdx.x][1], 1);
+        fence_mbar_init();
+    }
     __syncthreads();
     if (warp == 0) rowq_parse<SNAPPY>(sh, src, nunits, ticket, lane);
     else rowq_copy(sh, src, warp - 1, lane);

@@ -272,10 +272,14 @@ int64_t run_codec(bool compress, int codec, char* in, size_t in_size, char* out,
 }
 
 bool served(aocl_compression_type t) { return t == LZ4 || t == SNAPPY; }
+// LZ4HC streams are plain LZ4 blocks; the reference decodes them with the LZ4 decoder (api/codec.h:168 puts
+// aocl_lz4_decompress in the lz4hc row, api/codec.cpp:180-188).  The HC encoder itself is not on the path.
+bool served_decode(aocl_compression_type t) { return served(t) || t == LZ4HC; }
 
 }  // namespace
 
 extern "C" int64_t aocl_llc_compress(aocl_compression_desc* h, aocl_compression_type codec_type) {
+    if (h && codec_type == LZ4HC) return ERR_EXCLUDED_METHOD;   // decode-only codec id (the HC encoder is not built)
     if (!h || !served(codec_type)) return ERR_COMPRESSION_FAILED;
     const uint64_t t0 = now_ns();
     int64_t ret = run_codec(true, (int)codec_type, h->inBuf, h->inSize, h->outBuf, h->outSize);
@@ -290,9 +294,9 @@ extern "C" int64_t aocl_llc_compress(aocl_compression_desc* h, aocl_compression_
 }
 
 extern "C" int64_t aocl_llc_decompress(aocl_compression_desc* h, aocl_compression_type codec_type) {
-    if (!h || !served(codec_type)) return ERR_COMPRESSION_FAILED;
+    if (!h || !served_decode(codec_type)) return ERR_COMPRESSION_FAILED;
     const uint64_t t0 = now_ns();
-    const int64_t ret = run_codec(false, (int)codec_type, h->inBuf, h->inSize, h->outBuf, h->outSize);
+    const int64_t ret = run_codec(false, codec_type == LZ4HC ? (int)LZ4 : (int)codec_type, h->inBuf, h->inSize, h->outBuf, h->outSize);
     const uint64_t t1 = now_ns();
     if (h->measureStats == 1) {                               // api/api.cpp:110-116
         h->dSize = (uint64_t)ret;
@@ -306,7 +310,7 @@ extern "C" int32_t aocl_llc_setup(aocl_compression_desc* h, aocl_compression_typ
     if ((int)codec_type < (int)LZ4 || (int)codec_type >= (int)AOCL_COMPRESSOR_ALGOS_NUM) return ERR_UNSUPPORTED_METHOD;   // api/api.cpp:133-138
     if (!h) return ERR_INVALID_INPUT;
     h->optLevel = 4;                                          // utils/utils.cpp:148-172 overwrites the caller's value
-    if (!served(codec_type)) return ERR_EXCLUDED_METHOD;      // api/api.cpp:156-162
+    if (!served_decode(codec_type)) return ERR_EXCLUDED_METHOD;   // api/api.cpp:156-162
     std::lock_guard<std::mutex> lock(g.mu);
     if (codec_type == LZ4 && !g.lz4_setup_done) {
         // optOff (or AOCL_DISABLE_OPT=ON, utils/utils.cpp:207-219) selects the reference's

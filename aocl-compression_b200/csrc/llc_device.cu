@@ -243,12 +243,12 @@ extern "C" int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t c, int32_t cod
     }
     if (!ensure_ws(c, sizeof(PartDesc) * kMaxPartitions)) { c->last_rc = -2; return -2; }
     PartDesc* parts = reinterpret_cast<PartDesc*>(c->ws);
-    const bool ranged = !(first == 0 && count == 0xffffffffu);
-    // for a range the capacity check applies to the range, not to the whole stream
-    LLC_LAUNCH(rap_parse_kernel, 1, 1024, 0, c->stream, codec, (const uint8_t*)d_in, (uint64_t)n,
-               ranged ? ~0ull : (uint64_t)out_cap, parts, c->d_res);
+    const bool ranged = !(first == 0 && count == 0xffffffffu) || out_origin != 0;
+    LLC_LAUNCH(rap_parse_kernel, 1, 1024, 0, c->stream, codec, (const uint8_t*)d_in, (uint64_t)n, (uint64_t)out_cap,
+               ranged ? 0 : 1, parts, c->d_res);
+    // a range is validated against the caller's buffer before anything is decoded (the entries are untrusted)
+    if (ranged) LLC_LAUNCH(range_check_kernel, 1, 256, 0, c->stream, parts, c->d_res, first, count, out_origin, (uint64_t)out_cap);
     launch_decode_range(c, codec, d_in, d_out, parts, first, count, out_origin);
-    if (ranged) LLC_LAUNCH(range_total_kernel, 1, 256, 0, c->stream, parts, c->d_res, first, count);
     end_call(c);
     return 0;
 }
@@ -293,7 +293,7 @@ extern "C" int32_t aocl_gpu_decompress_open_async(aocl_gpu_ctx_t c, int32_t code
     begin_call(c);
     if ((codec != AOCL_GPU_LZ4 && codec != AOCL_GPU_SNAPPY) || !d_in || n == 0 || n > 0xffffffffull) { c->last_rc = -2; return -2; }
     if (!ensure_ws(c, sizeof(PartDesc) * kMaxPartitions)) { c->last_rc = -2; return -2; }
-    LLC_LAUNCH(rap_parse_kernel, 1, 1024, 0, c->stream, codec, (const uint8_t*)d_in, (uint64_t)n, (uint64_t)out_cap,
+    LLC_LAUNCH(rap_parse_kernel, 1, 1024, 0, c->stream, codec, (const uint8_t*)d_in, (uint64_t)n, (uint64_t)out_cap, 1,
                reinterpret_cast<PartDesc*>(c->ws), c->d_res);
     return 0;
 }

@@ -51,8 +51,10 @@ __device__ inline uint64_t block_excl_scan(uint64_t v, uint64_t* total, uint64_t
 // snappy.cc:2351-2366): partitions are decoded straight to their final offsets.
 // One CTA of 1024 threads.
 // ------------------------------------------------------------------------------------------
+// `check_total` = 0 for a ranged decode: the capacity then applies to the range (range_check_kernel), not to the
+// whole stream; a frame-less stream is always bounded by out_cap.
 __global__ void __launch_bounds__(1024) rap_parse_kernel(int codec, const uint8_t* __restrict__ in, uint64_t n,
-                                                         uint64_t out_cap, PartDesc* parts, CallResult* res) {
+                                                         uint64_t out_cap, int check_total, PartDesc* parts, CallResult* res) {
     __shared__ uint64_t sm[40];
     __shared__ uint32_t s_T, s_frame, s_bad;
     const int tid = threadIdx.x;
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(1024) rap_parse_kernel(int codec, const uint8_
     if (bad) atomicOr(&s_bad, 1u);
     __syncthreads();
     if (tid == 0) {
-        bool fail = s_bad || total > out_cap;
+        bool fail = s_bad || (check_total && total > out_cap);
         if (codec != 0 && !fail) {                              // Snappy: varint(total) follows the frame
             uint32_t v = 0;
             const uint32_t vb = frame <= n ? get_varint32(in + frame, n - frame, &v) : 0;
@@ -275,21 +277,36 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_pages_rowq_kernel(const u
     rowq_run<SNAPPY>(sh, src, count, &res->next);
 }
 
-// Range decode needs the byte count of the range rather than of the whole stream.
-__global__ void range_total_kernel(const PartDesc* __restrict__ parts, CallResult* res, uint32_t first, uint32_t count) {
-    if (res->error) return;
-    const uint32_t T = (uint32_t)res->parts;
-    const uint32_t end = min(T, first + min(count, T));
-    unsigned long long sum = 0;
-    for (uint32_t i = first + threadIdx.x; i < end; i += blockDim.x)
-        if (parts[i].in_len) sum += parts[i].out_len;
-    for (int d = 16; d; d >>= 1) sum += __shfl_down_sync(kFull, sum, d);
+// Ranged decode (a rank decoding its share of a frame, aocl_gpu_decompress_range_async): runs BEFORE the decode
+// kernels.  The RAP entries are untrusted, so every partition of the range must land inside the caller's buffer
+// [out, out + out_cap) once shifted by `origin`; otherwise the call fails and the decode kernels return at once.
+// Also replaces the stream total by the byte count of the range.
+__global__ void __launch_bounds__(256) range_check_kernel(const PartDesc* __restrict__ parts, CallResult* res, uint32_t first,
+                                                          uint32_t count, uint64_t origin, uint64_t out_cap) {
     __shared__ unsigned long long acc;
-    if (threadIdx.x == 0) acc = 0;
+    __shared__ int bad;
+    if (threadIdx.x == 0) { acc = 0; bad = 0; }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) atomicAdd(&acc, sum);
+    if (res->error == 0) {                                    // (read-only here: uniform for the whole CTA)
+        const uint32_t T = (uint32_t)res->parts;
+        const uint32_t end = min(T, first + min(count, T));
+        unsigned long long sum = 0;
+        bool oob = false;
+        for (uint32_t i = first + threadIdx.x; i < end; i += blockDim.x) {
+            const PartDesc d = parts[i];
+            if (!d.in_len) continue;
+            sum += d.out_len;
+            if (d.out_off < origin || d.out_off - origin > out_cap || (uint64_t)d.out_len > out_cap - (d.out_off - origin)) oob = true;
+        }
+        for (int k = 16; k; k >>= 1) sum += __shfl_down_sync(kFull, sum, k);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&acc, sum);
+        if (oob) bad = 1;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) res->value = (long long)acc;
+    if (threadIdx.x == 0 && res->error == 0) {
+        if (bad) { res->error = 1; res->value = kErrCorrupt; }
+        else res->value = (long long)acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

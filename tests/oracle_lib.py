@@ -18,7 +18,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libaocl_ref.so")
 
-LZ4, SNAPPY = 0, 4
+LZ4, LZ4HC, SNAPPY = 0, 1, 4
 
 
 def _u8p(a: np.ndarray):
@@ -160,13 +160,20 @@ class LlcLib:
         r = self.L.aocl_llc_compress(C.byref(d), codec)
         return r, (dst[:r].tobytes() if r > 0 else b"")
 
+    GUARD = 256
+
     def decompress(self, data, codec, cap, desc=None) -> tuple[int, bytes]:
+        """The destination sits between two guard regions; a call that touches them fails the test."""
         src = as_u8(data)
-        dst = np.zeros(max(cap, 1), dtype=np.uint8)
+        g = self.GUARD
+        buf = np.full(g + max(cap, 1) + g, 0xA5, dtype=np.uint8)
+        dst = buf[g:g + max(cap, 1)]
+        dst[:] = 0
         d = desc or self.new_desc(codec)
         d.inBuf, d.inSize = src.ctypes.data, len(src)
         d.outBuf, d.outSize = dst.ctypes.data, cap
         r = self.L.aocl_llc_decompress(C.byref(d), codec)
+        assert bool((buf[:g] == 0xA5).all()) and bool((buf[g + max(cap, 1):] == 0xA5).all()), "wrote outside the destination"
         return r, (dst[:r].tobytes() if r > 0 else b"")
 
 
