@@ -39,15 +39,21 @@ namespace llc {
 
 constexpr int kQSlots = 28;                                  // units in flight per CTA = copier warps
 constexpr int kQThreads = 32 * (kQSlots + 1);
-constexpr uint32_t kQCap = 64, kQMask = kQCap - 1;           // records per unit queue
-constexpr uint32_t kQStride = kQCap + 1;                     // +1 record: parser lanes hit different banks
+constexpr uint32_t kQCap = 64, kQMask = kQCap - 1;           // 32-bit entries per unit queue
+constexpr uint32_t kQStride = kQCap + 1;                     // +1 entry: parser lanes hit different banks
+constexpr uint32_t kQRoom = 8;                               // free entries a lane wants before it pushes a marker
 constexpr uint32_t kORing = 4096, kORingMask = kORing - 1;   // output bytes kept in shared memory per unit
-constexpr uint32_t kQMarker = 0xffffffffu;                   // rec.y of a marker record: rec.w = kind, rec.x = argument
-constexpr uint32_t kQBegin = 1u, kQQuit = 2u;
-constexpr uint32_t kQCapMax = 0xfffe0000u;                  // positions + ring size must not wrap
-constexpr uint32_t kPChunkLog = 8, kPChunk = 1u << kPChunkLog;   // parser window: two 256-byte chunks per unit
-constexpr uint32_t kPWin = 2 * kPChunk, kPWinMask = kPWin - 1;
-constexpr uint32_t kPReach = 72;                             // a fast step reads stream bytes [ip, ip + kPReach)
+// Queue entries: a stream position (of a token / element the fast step accepted) or a marker followed by its payload.
+constexpr uint32_t kMarkBase = 0xfffffff0u;
+constexpr uint32_t kMarkBegin = kMarkBase + 0;               // + unit index
+constexpr uint32_t kMarkSeq = kMarkBase + 1;                 // + literal position, literal length, offset, match length
+constexpr uint32_t kMarkEnd = kMarkBase + 2;                 // + failed (0 / 1), bytes produced
+constexpr uint32_t kMarkQuit = kMarkBase + 3;
+constexpr uint32_t kQCapMax = 0xfffe0000u;                   // output positions + ring size must not wrap
+constexpr uint32_t kQInMax = 0xffffff00u;                    // stream positions stay below the marker codes
+constexpr uint32_t kPChunkLog = 8, kPChunk = 1u << kPChunkLog;   // parser window: four 256-byte chunks per unit
+constexpr uint32_t kPChunks = 4, kPWin = kPChunks * kPChunk, kPWinMask = kPWin - 1;
+constexpr uint32_t kQReach = 80;                             // a fast step touches stream bytes [ip, ip + kQReach)
 constexpr uint32_t kQSpinMax = 1u << 20;                     // copier watchdog (~1 s of sleeping polls)
 constexpr uint32_t kUnitBad = 0x100u;                        // QUnit.flags: the unit header itself is malformed
 
@@ -55,12 +61,12 @@ struct QShared {
     alignas(128) uint8_t oring[kQSlots][kORing];
     alignas(128) uint8_t idata[kQSlots][kRingBytes];
     alignas(128) uint8_t pwin[kQSlots][kPWin];               // parser lanes' own view of their streams (TMA fed)
-    uint4 q[kQSlots * kQStride];
+    uint32_t q[kQSlots * kQStride];
     alignas(8) uint64_t ibar[kQSlots][kStages];
-    alignas(8) uint64_t pbar[kQSlots][2];
-    volatile uint32_t tail[kQSlots];                         // records published by the parser lane
-    volatile uint32_t head[kQSlots];                         // records retired by the copier
-    volatile uint32_t done[kQSlots];                         // the parser lane has published its last record
+    alignas(8) uint64_t pbar[kQSlots][kPChunks];
+    volatile uint32_t tail[kQSlots];                         // entries published by the parser lane
+    volatile uint32_t head[kQSlots];                         // entries retired by the copier
+    volatile uint32_t done[kQSlots];                         // the parser lane has published its last entry
     volatile uint32_t abort;                                 // watchdog: a queue made no progress, everybody leaves
 };
 static_assert(sizeof(QShared) <= 227 * 1024, "row decoder shared memory");
@@ -107,131 +113,111 @@ struct QPagesSource {
 // Per-lane parser state (registers).  Positions are offsets from gbase, the 16-byte aligned address at or below
 // the unit's first byte (the unit starts at position `pad`).
 //
-// The lane reads its stream through a private two-chunk window in shared memory that it fills itself with the
-// TMA bulk-copy engine: 32 lanes that walk 32 different streams through L1 in lock step pay somebody's cache
-// miss in almost every iteration (measured: ~1 us per sequence); from shared memory an iteration costs one
-// 30-cycle load.  `lo` is the chunk that holds ip, `hi` the highest chunk known to have landed (lo or lo + 1);
-// chunk lo + 1 is always in flight or landed, and entering it frees the buffer of chunk lo for chunk lo + 2.
+// The lane reads its stream through a private four-chunk window in shared memory that it fills itself with the
+// TMA bulk-copy engine: 28 lanes that walk 28 different streams through L1 in lock step pay somebody's cache
+// miss in almost every iteration (measured: ~1 us per sequence); from shared memory a step costs one 30-cycle
+// load.  Chunks [.., w_issued) have been requested, chunks [.., w_landed) are known to have arrived; stream
+// bytes below wlim may be read.
 struct QLane {
     const uint8_t* gbase;
     uint32_t ip, iend, op, cap;        // iend: stream end (relative to gbase)
     uint32_t fast_i_ex, fast_o_ex;     // exclusive bounds of the region where no end rule can fire
     uint32_t pad;
     uint32_t wbase;                    // shared-space address of the window
-    uint64_t* bar;                     // its two mbarriers
-    uint32_t lo, hi, pstate;           // pstate: bits 0-1 parity of the next phase per buffer, bits 2-3 load pending
+    uint32_t bar0;                     // shared-space address of its first mbarrier
+    uint32_t w_issued, w_landed, wlim, wpar;   // wpar: bit b = parity of the next phase of buffer b
     bool last, bad;
 };
 
-__device__ __forceinline__ void qwin_wait(QLane& s, uint32_t b) {
-    if (s.pstate & (4u << b)) {
-        while (!mbar_try_wait(&s.bar[b], (s.pstate >> b) & 1u)) {}
-        s.pstate ^= (1u << b) | (4u << b);
-    }
-}
 __device__ __forceinline__ void qwin_issue(QLane& s, uint32_t c) {
-    const uint32_t base = c << kPChunkLog, b = c & 1u;
-    if (base >= s.iend) return;
-    const uint32_t left = s.iend - base;
+    const uint32_t base = c << kPChunkLog, b = c & (kPChunks - 1u);
+    const uint32_t left = s.iend - base;                    // caller: base < iend
     const uint32_t bytes = left >= kPChunk ? kPChunk : ((left + 15u) & ~15u);
+    const uint32_t bar = s.bar0 + 8u * b;
     fence_proxy_async();                                     // my earlier reads of this buffer come first
-    mbar_expect_tx(&s.bar[b], bytes);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(s.wbase + b * kPChunk), "l"(s.gbase + base), "r"(bytes), "r"(smem_u32(&s.bar[b])) : "memory");
-    s.pstate |= 4u << b;
+                 ::"r"(s.wbase + b * kPChunk), "l"(s.gbase + base), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void qwin_wait(QLane& s, uint32_t c) {
+    const uint32_t b = c & (kPChunks - 1u), bar = s.bar0 + 8u * b, parity = (s.wpar >> b) & 1u;
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+    s.wpar ^= 1u << b;
+}
+// Keep chunks up to (chunk of ip) + 2 requested and up to (chunk of ip) + 1 landed.  A chunk goes into buffer
+// (chunk & 3), i.e. over chunk - 4, which lies behind ip.
+__device__ __forceinline__ void qwin_fill(QLane& s) {
+    const uint32_t c = s.ip >> kPChunkLog;
+    while (s.w_issued < c + 3u && (s.w_issued << kPChunkLog) < s.iend) { qwin_issue(s, s.w_issued); s.w_issued++; }
+    const uint32_t want = min(c + 2u, s.w_issued);
+    while (s.w_landed < want) { qwin_wait(s, s.w_landed); s.w_landed++; }
+    s.wlim = s.w_landed << kPChunkLog;
+}
+// wait for everything in flight (before the buffers are reused for another place of the stream / another unit)
+__device__ __forceinline__ void qwin_drain(QLane& s) {
+    while (s.w_landed < s.w_issued) { qwin_wait(s, s.w_landed); s.w_landed++; }
 }
 // (re)start the window at the chunk of s.ip
 __device__ __forceinline__ void qwin_open(QLane& s) {
-    qwin_wait(s, 0); qwin_wait(s, 1);
-    const uint32_t c = s.ip >> kPChunkLog;
-    s.lo = s.hi = c;
-    qwin_issue(s, c); qwin_issue(s, c + 1u);
-    qwin_wait(s, c & 1u);
+    qwin_drain(s);
+    s.w_issued = s.w_landed = s.ip >> kPChunkLog;
+    qwin_fill(s);
 }
-// before a fast step at s.ip: every byte of [ip, ip + kPReach) has landed
-__device__ __forceinline__ void qwin_step(QLane& s) {
-    const uint32_t c = s.ip >> kPChunkLog, need = (s.ip + kPReach - 1u) >> kPChunkLog;
-    if (c != s.lo) { s.lo = c; qwin_issue(s, c + 1u); }      // chunk c - 1 is behind me: its buffer takes chunk c + 1
-    if (need != s.hi) { qwin_wait(s, need & 1u); s.hi = need; }
-}
-// 8 stream bytes at position p from the window (any alignment, wraps)
-__device__ __forceinline__ uint64_t qwin_ld64(const QLane& s, uint32_t p) {
-    const uint32_t a = p & ~3u;
-    const unsigned sh = (p & 3u) * 8u;
-    uint32_t w0, w1, w2;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(s.wbase + (a & kPWinMask)));
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(s.wbase + ((a + 4u) & kPWinMask)));
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(s.wbase + ((a + 8u) & kPWinMask)));
-    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
-}
-__device__ __forceinline__ uint32_t qwin_ld32(const QLane& s, uint32_t p) {
-    const uint32_t a = p & ~3u;
-    uint32_t w0, w1;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(s.wbase + (a & kPWinMask)));
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(s.wbase + ((a + 4u) & kPWinMask)));
-    return __funnelshift_r(w0, w1, (p & 3u) * 8u);
-}
+__device__ __forceinline__ uint32_t qwin_u8(const QLane& s, uint32_t p) { return lds_u8(s.wbase + (p & kPWinMask)); }
 
-__device__ __forceinline__ void qpush(uint4* q, uint32_t& tail, uint32_t lp, uint32_t ll, uint32_t off, uint32_t ml) {
-    q[tail & kQMask] = make_uint4(lp, ll, off, ml);
-    tail++;
-}
-
-// FAST STEP, LZ4.  Precondition: ip < fast_i_ex and op < fast_o_ex -- at least 319 stream bytes and 559 output
-// bytes ahead, so a sequence with at most one length byte each (ll <= 269, ml <= 273) cannot trigger an
-// end-of-block rule -- and qwin_step() has been called.  Straight-line code.  Returns 0: consumed, 1: not
-// consumed (a 255 length byte or a literal run too long for the window: take the general step), 2: corrupt.
-// Record positions are relative to the unit's first byte.
-__device__ __forceinline__ int qlane_fast_lz4(QLane& s, uint4* q, uint32_t& tail) {
+// FAST STEP, LZ4: accept the sequence at ip knowing only where it ends; its fields are read again, lane per
+// sequence, by the copier.  Precondition: ip < fast_i_ex and op < fast_o_ex -- at least 319 stream bytes and 559
+// output bytes ahead, so a sequence with at most one length byte each (ll <= 269, ml <= 273) cannot trigger an
+// end-of-block rule -- and ip + kQReach <= wlim.  Straight-line code, three independent-address loads.
+// Returns false (nothing consumed) for a 255 length byte or a literal run beyond the reach: general step.
+__device__ __forceinline__ bool qfast_lz4(QLane& s, uint32_t* q, uint32_t& tail) {
     const uint32_t ip = s.ip;
-    const uint64_t w = qwin_ld64(s, ip);
-    const uint32_t w0 = (uint32_t)w;
-    const uint32_t tok = w0 & 0xffu, e1 = (w0 >> 8) & 0xffu;
+    const uint32_t tok = qwin_u8(s, ip), e1 = qwin_u8(s, ip + 1u);
     const uint32_t nibL = tok >> 4, nibM = tok & 15u;
     const bool extL = nibL == 15u, extM = nibM == 15u;
-    const uint32_t ll = nibL + (extL ? e1 : 0u);
-    const uint32_t hdr = 1u + (extL ? 1u : 0u);
-    const uint32_t rel = hdr + ll;                          // the offset field, relative to ip
-    if (rel > kPReach - 4u) return 1;
-    uint32_t t = (uint32_t)(w >> (8u * (rel & 7u)));        // offset (2 bytes) and the byte after it
-    if (rel > 5u) t = qwin_ld32(s, ip + rel);
-    const uint32_t off = t & 0xffffu, e2 = (t >> 16) & 0xffu;
+    const uint32_t ll = extL ? 15u + e1 : nibL;
+    const uint32_t rel = ll + (extL ? 2u : 1u);             // the offset field, relative to ip
+    const uint32_t e2 = qwin_u8(s, ip + rel + 2u);          // (garbage when rel is out of reach: rejected below)
     const uint32_t ml = nibM + 4u + (extM ? e2 : 0u);
-    const uint32_t op2 = s.op + ll;
-    const bool special = (extL & (e1 == 255u)) | (extM & (e2 == 255u));
-    const bool badoff = (off - 1u) >= op2;                  // lz4.c:4196-4197
-    if (special | badoff) return special ? 1 : 2;
-    qpush(q, tail, ip + hdr - s.pad, ll, off, ml);
-    s.op = op2 + ml;
+    if ((extL & (e1 == 255u)) | (extM & (e2 == 255u)) | (rel + 3u > kQReach)) return false;
+    q[tail & kQMask] = ip;
+    tail++;
+    s.op += ll + ml;
     s.ip = ip + rel + 2u + (extM ? 1u : 0u);
-    return 0;
+    return true;
 }
-
-// FAST STEP, Snappy.  Precondition: ip < fast_i_ex (319 stream bytes ahead), qwin_step() called.  Returns as
-// qlane_fast_lz4 (1: a 4-byte-offset copy or a literal with length bytes: take the general step).
-__device__ __forceinline__ int qlane_fast_snappy(QLane& s, uint4* q, uint32_t& tail) {
-    const uint32_t ip = s.ip, expect = s.cap;
-    const uint32_t w0 = qwin_ld32(s, ip);
-    const uint32_t tag = w0 & 0xffu, b1 = (w0 >> 8) & 0xffu, b2 = (w0 >> 16) & 0xffu;
+// FAST STEP, Snappy.  Precondition: ip < fast_i_ex (319 stream bytes ahead), ip + kQReach <= wlim.  Returns false
+// for a 4-byte-offset copy, a literal with length bytes, or an element that does not fit the output: general step.
+__device__ __forceinline__ bool qfast_snappy(QLane& s, uint32_t* q, uint32_t& tail) {
+    const uint32_t ip = s.ip;
+    const uint32_t tag = qwin_u8(s, ip);
     const uint32_t kind = tag & 3u, hi = tag >> 2;
     const bool is_lit = kind == 0u;
-    const uint32_t lit_len = hi + 1u;
-    const uint32_t cp_len = (kind == 1u) ? 4u + (hi & 7u) : 1u + hi;
-    const uint32_t cp_off = (kind == 1u) ? (((tag >> 5) << 8) | b1) : (b1 | (b2 << 8));
-    const uint32_t len = is_lit ? lit_len : cp_len;
-    const bool special = (kind == 3u) | (is_lit & (hi >= 60u - 0u)) | (is_lit & (lit_len > kPReach - 4u));
-    const bool badel = (len > expect - s.op) | (!is_lit & ((cp_off - 1u) >= s.op));   // snappy.cc:2185-2199
-    if (special | badel) return special ? 1 : 2;
-    qpush(q, tail, ip + 1u - s.pad, is_lit ? lit_len : 0u, is_lit ? 0u : cp_off, is_lit ? 0u : cp_len);
+    const uint32_t len = (kind == 1u) ? 4u + (hi & 7u) : hi + 1u;
+    const uint32_t adv = is_lit ? 1u + len : (kind == 1u ? 2u : 3u);
+    if ((kind == 3u) | (is_lit & (hi >= 60u)) | (len > s.cap - s.op)) return false;
+    q[tail & kQMask] = ip;
+    tail++;
     s.op += len;
-    s.ip = ip + (is_lit ? 1u + lit_len : (kind == 1u ? 2u : 3u));
-    return 0;
+    s.ip = ip + adv;
+    return true;
+}
+
+// Marker with a fully parsed sequence (the general steps below; positions relative to the unit's first byte)
+__device__ __forceinline__ void qpush_seq(const QLane& s, uint32_t* q, uint32_t& tail, uint32_t lp, uint32_t ll, uint32_t off, uint32_t ml) {
+    q[tail & kQMask] = kMarkSeq; q[(tail + 1u) & kQMask] = lp + s.pad; q[(tail + 2u) & kQMask] = ll;
+    q[(tail + 3u) & kQMask] = off; q[(tail + 4u) & kQMask] = ml;
+    tail += 5u;
 }
 
 // One LZ4 sequence through the general code (bytes straight from global memory): length runs, block tail, tiny
 // units -- every check of the reference.  Returns false when the unit is finished (ok or bad).  Positions in the
 // lane state are relative to gbase; the arithmetic below is relative to the unit's first byte.
-__device__ __noinline__ bool qlane_step_lz4(QLane& s, uint4* q, uint32_t& tail) {
+__device__ __noinline__ bool qlane_step_lz4(QLane& s, uint32_t* q, uint32_t& tail) {
     const uint8_t* in = s.gbase + s.pad;
     const uint32_t ip = s.ip - s.pad;
     const uint32_t iend = s.iend - s.pad, cap = s.cap;
@@ -251,7 +237,7 @@ __device__ __noinline__ bool qlane_step_lz4(QLane& s, uint4* q, uint32_t& tail) 
     s.op += ll;
     const uint32_t qq = p + ll;
     if ((closing && (last || s.op == cap)) || qq == iend) {
-        if (ll) qpush(q, tail, lit_pos, ll, 0, 0);
+        if (ll) qpush_seq(s, q, tail, lit_pos, ll, 0, 0);
         s.ip = qq + s.pad;
         return false;
     }
@@ -266,7 +252,7 @@ __device__ __noinline__ bool qlane_step_lz4(QLane& s, uint4* q, uint32_t& tail) 
     ml += 4;
     if (off == 0 || off > s.op || ml > cap - s.op) { s.bad = true; return false; }   // lz4.c:4196-4197
     if (last && (uint64_t)s.op + ml + 5 > cap) { s.bad = true; return false; }       // lz4.c:4262-4264
-    qpush(q, tail, lit_pos, ll, off, ml);
+    qpush_seq(s, q, tail, lit_pos, ll, off, ml);
     s.op += ml;
     s.ip = p + s.pad;
     if (!last && (s.op == cap || p >= iend)) return false;                           // lz4.c:4285-4288
@@ -274,13 +260,13 @@ __device__ __noinline__ bool qlane_step_lz4(QLane& s, uint4* q, uint32_t& tail) 
 }
 
 // One Snappy element through the general code (cap is the exact size the stream must produce).
-__device__ __noinline__ bool qlane_step_snappy(QLane& s, uint4* q, uint32_t& tail) {
+__device__ __noinline__ bool qlane_step_snappy(QLane& s, uint32_t* q, uint32_t& tail) {
     const uint8_t* in = s.gbase + s.pad;
     const uint32_t ip = s.ip - s.pad, iend = s.iend - s.pad, expect = s.cap;
     if (ip >= iend) return false;
     const uint32_t tag = in[ip];
     const uint32_t kind = tag & 3u, hi = tag >> 2;
-    uint32_t len, off = 0, nip;
+    uint32_t len, nip;
     if (kind == 0u) {                                   // literal, snappy.cc:1492-1527
         uint32_t p = ip + 1u;
         len = hi + 1u;
@@ -293,10 +279,10 @@ __device__ __noinline__ bool qlane_step_snappy(QLane& s, uint4* q, uint32_t& tai
             len = v + 1u; p += nb;
         }
         if (len > iend - p || len > expect - s.op) { s.bad = true; return false; }
-        qpush(q, tail, p, len, 0, 0);
+        qpush_seq(s, q, tail, p, len, 0, 0);
         nip = p + len;
     } else {                                            // char_table, snappy-internal.h:406-439
-        uint32_t adv;
+        uint32_t adv, off;
         if (kind == 1u) {
             if (ip + 2 > iend) { s.bad = true; return false; }
             len = 4u + (hi & 7u); off = ((tag >> 5) << 8) | in[ip + 1]; adv = 2;
@@ -310,7 +296,7 @@ __device__ __noinline__ bool qlane_step_snappy(QLane& s, uint4* q, uint32_t& tai
             adv = 5;
         }
         if (off == 0 || off > s.op || len > expect - s.op) { s.bad = true; return false; }   // snappy.cc:2185-2199
-        qpush(q, tail, ip + 1u, 0, off, len);
+        qpush_seq(s, q, tail, ip + 1u, 0, off, len);
         nip = ip + adv;
     }
     s.op += len;
@@ -318,53 +304,52 @@ __device__ __noinline__ bool qlane_step_snappy(QLane& s, uint4* q, uint32_t& tai
     return true;
 }
 
-// The parser warp: lane l owns slot l.  A lane that finishes a unit reports its result and draws the next
-// one: the first unit of every slot is assigned statically (interleaved over the grid, so that a frame
-// with fewer units than slots spreads over all SMs), later ones come from the atomic ticket.
+// The parser warp: lane l owns slot l.  A lane that finishes a unit pushes the END marker (the copier reports the
+// result: it validates the offsets of the fast sequences) and draws the next unit: the first unit of every slot is
+// assigned statically (interleaved over the grid, so that a frame with fewer units than slots spreads over all
+// SMs), later ones come from the atomic ticket.
 template <bool SNAPPY, class Src>
 __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, unsigned int* ticket, int lane) {
     const int slot = lane < kQSlots ? lane : 0;
-    uint4* const q = sh.q + slot * kQStride;
+    uint32_t* const q = sh.q + slot * kQStride;
     QLane s;
     QUnit u;
     s.gbase = nullptr; s.ip = s.iend = s.op = s.cap = s.fast_i_ex = s.fast_o_ex = s.pad = 0;
-    s.wbase = smem_u32(sh.pwin[slot]); s.bar = sh.pbar[slot];
-    s.lo = s.hi = 0; s.pstate = 0;
+    s.wbase = smem_u32(sh.pwin[slot]); s.bar0 = smem_u32(&sh.pbar[slot][0]);
+    s.w_issued = s.w_landed = s.wlim = s.wpar = 0;
     s.last = false; s.bad = false;
     u.in = nullptr; u.out = nullptr; u.clen = u.cap = u.flags = 0;
-    uint32_t tail = 0, published = 0, head_c = 0, cur = 0;
+    uint32_t tail = 0, published = 0, head_c = 0;
     bool active = false, alive = lane < kQSlots, first_fetch = true;
     while (__any_sync(kFull, alive)) {
         if (sh.abort) break;
-        bool moved = false;
         // ---- fast steps: up to 8 sequences per lane back to back (the bookkeeping below runs once per pass)
         bool slow = !active;                                 // this lane needs the general code
 #pragma unroll 1
         for (int it = 0; it < 8; it++) {
-            const bool can = active && !slow && (tail - head_c < kQCap) && s.ip < s.fast_i_ex && (SNAPPY || s.op < s.fast_o_ex);
+            const bool can = active && !slow && (tail - head_c < kQCap) && s.ip < s.fast_i_ex && (SNAPPY || s.op < s.fast_o_ex) &&
+                             s.ip + kQReach <= s.wlim;
             if (!__any_sync(kFull, can)) break;
-            if (can) {
-                qwin_step(s);
-                const int r = SNAPPY ? qlane_fast_snappy(s, q, tail) : qlane_fast_lz4(s, q, tail);
-                if (r) { slow = true; if (r == 2) s.bad = true; }
-                moved = true;
-            }
+            if (can && !(SNAPPY ? qfast_snappy(s, q, tail) : qfast_lz4(s, q, tail))) slow = true;
         }
+        bool moved = false;
         if (alive) {
-            if (tail - head_c >= kQCap) head_c = sh.head[lane];
-            const bool room = tail - head_c < kQCap;
-            if (active && !slow && room && !(s.ip < s.fast_i_ex && (SNAPPY || s.op < s.fast_o_ex))) slow = true;   // left the fast region
+            if (tail - head_c + kQRoom > kQCap) head_c = sh.head[lane];
+            const bool room = tail - head_c + kQRoom <= kQCap;
+            moved = room;
+            if (active && !slow) {
+                if (s.ip < s.fast_i_ex && (SNAPPY || s.op < s.fast_o_ex)) qwin_fill(s);   // (usually nothing to do)
+                else slow = true;                                                        // left the fast region
+            }
             if (room && slow) {
-                moved = true;
                 if (!active) {
                     uint32_t i;
                     if (first_fetch) { i = (uint32_t)lane * gridDim.x + blockIdx.x; first_fetch = false; }
                     else i = gridDim.x * (uint32_t)kQSlots + atomicAdd(ticket, 1u);
                     if (i >= nunits) {
-                        qpush(q, tail, 0, kQMarker, 0, kQQuit);
+                        q[tail & kQMask] = kMarkQuit; tail++;
                         alive = false;
                     } else if (src.open(i, u)) {
-                        cur = i;
                         s.pad = (uint32_t)(reinterpret_cast<uintptr_t>(u.in) & 15);
                         s.gbase = u.in - s.pad;
                         s.iend = u.clen + s.pad; s.cap = min(u.cap, kQCapMax);
@@ -374,33 +359,33 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
                         s.fast_i_ex = any_fast ? s.iend - 319u : 0u;
                         s.fast_o_ex = (any_fast && !SNAPPY) ? s.cap - 559u : 0u;
                         bool run = true;
-                        if (u.flags & kUnitBad) { s.bad = true; run = false; }
+                        if ((u.flags & kUnitBad) || u.clen > kQInMax) { s.bad = true; run = false; }
                         else if (!SNAPPY) {
                             if (u.clen == 0) { s.bad = true; run = false; }
                             else if (s.cap == 0) { s.bad = !(u.clen == 1 && u.in[0] == 0); run = false; }   // lz4.c:3854-3858
                         }
+                        q[tail & kQMask] = kMarkBegin; q[(tail + 1u) & kQMask] = i; tail += 2u;
                         if (run) {
                             if (any_fast) qwin_open(s);
-                            qpush(q, tail, i, kQMarker, 0, kQBegin);
                             active = true;
-                        } else {
-                            src.report(cur, s.bad ? kErrCorrupt : 0, u);
+                        } else {                             // nothing to decode: BEGIN is followed by END right away
+                            q[tail & kQMask] = kMarkEnd; q[(tail + 1u) & kQMask] = s.bad ? 1u : 0u; q[(tail + 2u) & kQMask] = 0u; tail += 3u;
                         }
                     }
                 } else {
                     const bool more = !s.bad && (SNAPPY ? qlane_step_snappy(s, q, tail) : qlane_step_lz4(s, q, tail));
                     if (!more) {
-                        long long r = s.bad ? kErrCorrupt : (long long)s.op;
-                        if (!s.bad && SNAPPY && s.op != s.cap) r = kErrCorrupt;             // snappy.cc:1715
-                        src.report(cur, r, u);
+                        const bool failed = s.bad || (SNAPPY && s.op != s.cap);            // snappy.cc:1715
+                        q[tail & kQMask] = kMarkEnd; q[(tail + 1u) & kQMask] = failed ? 1u : 0u; q[(tail + 2u) & kQMask] = s.op; tail += 3u;
                         active = false;
-                    } else if (s.ip < s.fast_i_ex &&
-                               !((s.ip >> kPChunkLog) == s.lo && ((s.ip + kPReach - 1u) >> kPChunkLog) <= s.hi)) {
-                        qwin_open(s);                       // back to the fast steps, beyond what the window holds
+                    } else if (s.ip < s.fast_i_ex) {
+                        // back to the fast steps: restart the window unless ip is still inside what it holds
+                        if ((s.ip >> kPChunkLog) + 1u >= s.w_landed || (s.ip >> kPChunkLog) + kPChunks <= s.w_issued) qwin_open(s);
+                        else qwin_fill(s);
                     }
                 }
             }
-            if (tail - published >= 16u || (!active && tail != published)) {
+            if (tail - published >= 16u || (!(active && !slow) && tail != published)) {
                 __threadfence_block();
                 sh.tail[lane] = tail;
                 published = tail;
@@ -409,7 +394,7 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
         }
         if (!__any_sync(kFull, moved)) __nanosleep(200);    // every queue is full: the copiers are the bottleneck
     }
-    qwin_wait(s, 0); qwin_wait(s, 1);                       // nothing may stay in flight
+    qwin_drain(s);                                           // nothing may stay in flight
 }
 
 // ----------------------------------------------------------------------------------------- copiers
@@ -473,22 +458,31 @@ __device__ __forceinline__ void rowq_rows(const QBatch& B, int lane) {
     if (x0 < op_end) rowq_row<USE_RING, false>(B, x0, lane);                       // ... and ends inside one
 }
 
-// Executes the n (1..32) records held lane-per-record in `rec`; lanes >= n hold nothing.
-__device__ __forceinline__ void rowq_batch(Ring& ring, uint32_t obase, uint8_t* gout, uint32_t& op_io, uint32_t pad,
+// Executes the n (1..32) records held lane-per-record in `rec` = {literal position, literal length, offset,
+// match length}; lanes >= n hold nothing.  `a` is the position of the unit's first output byte: a match may not
+// reach before it (lz4.c:4196-4197, snappy.cc:2190-2191) -- the records of the fast steps are validated here,
+// lane per record.  Returns false when a record is bad (the records before it have been executed).
+__device__ __forceinline__ bool rowq_batch(Ring& ring, uint32_t obase, uint8_t* gout, uint32_t a, uint32_t& op_io,
                                            const uint4 rec, uint32_t n, int lane) {
     QBatch B;
     B.op = op_io;
-    const bool valid = (uint32_t)lane < n;
+    bool valid = (uint32_t)lane < n;
     const uint32_t ll = valid ? rec.y : 0u, ml = valid ? rec.w : 0u;
     const uint32_t len = ll + ml;
     const uint32_t incl = warp_incl_sum(len, lane);
-    B.total = __shfl_sync(kFull, incl, 31);
     const uint32_t d = B.op + incl - len;                    // first output byte of my record
-    B.D = valid ? d : 0xffffffffu;
     B.M = d + ll;
-    const uint32_t lpos = rec.x + pad;                       // literals of my record in ring coordinates
-    B.L = lpos - d;                                          // literal byte x of my record sits at ring position x + L
     B.O = rec.z;
+    const unsigned badmask = __ballot_sync(kFull, valid && ml != 0u && (B.O - 1u) >= B.M - a);
+    if (badmask) {
+        n = (uint32_t)__ffs(badmask) - 1u;
+        if (n == 0) return false;
+        valid = (uint32_t)lane < n;
+    }
+    B.total = __shfl_sync(kFull, incl, (int)n - 1) ;         // (all of it: lanes >= the original n add nothing)
+    B.D = valid ? d : 0xffffffffu;
+    const uint32_t lpos = rec.x;                             // literals of my record in ring coordinates
+    B.L = lpos - d;                                          // literal byte x of my record sits at ring position x + L
     B.lemask = ((2u << lane) - 1u) & ~1u;
     B.obase = obase; B.gout = gout;
     // literal window of the batch (positions grow with the lane): the TMA ring when it fits, else global loads
@@ -505,18 +499,42 @@ __device__ __forceinline__ void rowq_batch(Ring& ring, uint32_t obase, uint8_t* 
         rowq_rows<false>(B, lane);
     }
     op_io = B.op + B.total;
+    return badmask == 0;
+}
+
+// Lane per entry: the fields of the sequence / element whose token sits at stream position p (the parser's fast
+// step accepted it: at most one length byte each, everything within kQReach bytes, inside the stream).
+template <bool SNAPPY>
+__device__ __forceinline__ uint4 rowq_fields(const Ring& ring, uint32_t p) {
+    if (!SNAPPY) {
+        const uint32_t tok = ring.byte(p), e1 = ring.byte(p + 1u);
+        const uint32_t nibL = tok >> 4, nibM = tok & 15u;
+        const bool extL = nibL == 15u, extM = nibM == 15u;
+        const uint32_t ll = extL ? 15u + e1 : nibL;
+        const uint32_t lit = p + (extL ? 2u : 1u), qq = lit + ll;
+        const uint32_t off = ring.byte(qq) | (ring.byte(qq + 1u) << 8), e2 = ring.byte(qq + 2u);
+        return make_uint4(lit, ll, off, nibM + 4u + (extM ? e2 : 0u));
+    } else {
+        const uint32_t tag = ring.byte(p), b1 = ring.byte(p + 1u), b2 = ring.byte(p + 2u);
+        const uint32_t kind = tag & 3u, hi = tag >> 2;
+        if (kind == 0u) return make_uint4(p + 1u, hi + 1u, 0u, 0u);
+        if (kind == 1u) return make_uint4(p + 1u, 0u, ((tag >> 5) << 8) | b1, 4u + (hi & 7u));
+        return make_uint4(p + 1u, 0u, b1 | (b2 << 8), hi + 1u);
+    }
 }
 
 // A copier warp: consumes the queue of its slot until the parser's QUIT marker.
-template <class Src>
+template <bool SNAPPY, class Src>
 __device__ inline void rowq_copy(QShared& sh, const Src& src, int slot, int lane) {
     Ring ring;
     ring.init(sh.idata[slot], sh.ibar[slot], lane);
     const uint32_t obase = smem_u32(sh.oring[slot]);
-    const uint4* const q = sh.q + slot * kQStride;
-    uint32_t head = 0, op = 0, pad = 0;
+    const uint32_t* const q = sh.q + slot * kQStride;
+    uint32_t head = 0, op = 0, a = 0, unit = 0;
     uint8_t* gout = nullptr;
-    bool open = false;
+    QUnit u;
+    u.in = nullptr; u.out = nullptr; u.clen = u.cap = u.flags = 0;
+    bool open = false, ubad = false;
     for (;;) {
         // wait for a full batch (or for whatever is left once the parser lane is done); sleeping, not spinning:
         // a polling copier takes issue slots from the parser warp it is waiting for
@@ -536,34 +554,53 @@ __device__ inline void rowq_copy(QShared& sh, const Src& src, int slot, int lane
         if (avail == 0) break;
         __threadfence_block();
         uint32_t n = min(avail, 32u);
-        uint4 rec = make_uint4(0, 0, 0, 0);
-        if ((uint32_t)lane < n) rec = q[(head + lane) & kQMask];
-        const unsigned marks = __ballot_sync(kFull, (uint32_t)lane < n && rec.y == kQMarker);
-        if (marks) n = (uint32_t)__ffs(marks) - 1u;
-        if (n) rowq_batch(ring, obase, gout, op, pad, rec, n, lane);
-        head += n;
-        bool quit = false;
-        if (marks) {
-            const int mk = __ffs(marks) - 1;
-            const uint32_t kind = __shfl_sync(kFull, rec.w, mk), arg = __shfl_sync(kFull, rec.x, mk);
-            head += 1u;
-            if (open) { ring.close(); open = false; }
-            if (kind == kQQuit) quit = true;
-            else {
-                QUnit u;
-                src.open(arg, u);
-                const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(u.out) & 31);
+        const uint32_t e = (uint32_t)lane < n ? q[(head + lane) & kQMask] : 0u;
+        const unsigned marks = __ballot_sync(kFull, (uint32_t)lane < n && e >= kMarkBase);
+        uint32_t m = marks ? (uint32_t)__ffs(marks) - 1u : n;   // plain positions in front of the first marker
+        if (m) {
+            // keep what the input ring can hold at once (a fast sequence spans < kQReach bytes)
+            const uint32_t p0 = __shfl_sync(kFull, e, 0);
+            const uint32_t fit = (uint32_t)__popc(__ballot_sync(kFull, (uint32_t)lane < m && e + kQReach <= (p0 & ~(kChunk - 1u)) + kRingBytes));
+            if (fit < m) { m = fit; }
+            if (!ubad) {
+                ring.advance(p0, lane);
+                ring.ensure(__shfl_sync(kFull, e, (int)m - 1) + kQReach);
+                uint4 rec = make_uint4(0, 0, 0, 0);
+                if ((uint32_t)lane < m) rec = rowq_fields<SNAPPY>(ring, e);
+                if (!rowq_batch(ring, obase, gout, a, op, rec, m, lane)) ubad = true;
+            }
+            head += m;
+        } else {
+            const uint32_t code = __shfl_sync(kFull, e, 0);
+            // the parser publishes a marker together with its payload
+            const uint32_t w1 = q[(head + 1u) & kQMask], w2 = q[(head + 2u) & kQMask], w3 = q[(head + 3u) & kQMask], w4 = q[(head + 4u) & kQMask];
+            if (code == kMarkSeq) {
+                uint4 rec = make_uint4(0, 0, 0, 0);
+                if (lane == 0) rec = make_uint4(w1, w2, w3, w4);
+                if (!ubad && !rowq_batch(ring, obase, gout, a, op, rec, 1u, lane)) ubad = true;
+                head += 5u;
+            } else if (code == kMarkBegin) {
+                unit = w1;
+                src.open(unit, u);
+                a = (uint32_t)(reinterpret_cast<uintptr_t>(u.out) & 31);
                 gout = u.out - a;                            // rows are aligned 32-byte sectors of the output
                 op = a;
-                pad = ring.open(u.in, u.clen);
+                ubad = false;
+                if (open) ring.close();
+                ring.open(u.in, u.clen);
                 open = true;
+                head += 2u;
+            } else if (code == kMarkEnd) {
+                if (lane == 0) src.report(unit, (w1 != 0u || ubad) ? kErrCorrupt : (long long)w2, u);
+                head += 3u;
+            } else {                                         // kMarkQuit
+                break;
             }
         }
         __syncwarp();
         if (lane == 0) { __threadfence_block(); sh.head[slot] = head; }
-        if (quit) break;
     }
-    if (open) ring.close();                                  // (watchdog exit) nothing may stay in flight
+    if (open) ring.close();                                  // nothing may stay in flight
 }
 
 template <bool SNAPPY, class Src>
@@ -572,12 +609,12 @@ __device__ __forceinline__ void rowq_run(QShared& sh, const Src& src, uint32_t n
     if (threadIdx.x < kQSlots) { sh.tail[threadIdx.x] = 0; sh.head[threadIdx.x] = 0; sh.done[threadIdx.x] = 0; }
     if (threadIdx.x == 0) sh.abort = 0;
     if (threadIdx.x < kQSlots) {                             // parser windows: one mbarrier per buffer
-        mbar_init(&sh.pbar[threadIdx.x][0], 1); mbar_init(&sh.pbar[threadIdx.x][1], 1);
+        for (uint32_t b = 0; b < kPChunks; b++) mbar_init(&sh.pbar[threadIdx.x][b], 1);
         fence_mbar_init();
     }
     __syncthreads();
     if (warp == 0) rowq_parse<SNAPPY>(sh, src, nunits, ticket, lane);
-    else rowq_copy(sh, src, warp - 1, lane);
+    else rowq_copy<SNAPPY>(sh, src, warp - 1, lane);
 }
 
 }  // namespace llc

@@ -17,10 +17,12 @@
 #include "../../include/aocl_llc_native.h"
 
 #include <cuda_runtime.h>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 #include <time.h>
 
 #ifndef AOCL_LLC_BUILD_TAG
@@ -30,38 +32,143 @@
 namespace {
 
 constexpr uint64_t kRapMagic = 0x434C4C5F4C434F41ULL;
-
-struct Global {
-    std::mutex mu;                 // one in-flight call per process-wide context
-    aocl_gpu_ctx_t ctx = nullptr;
-    bool ctx_failed = false;
-    void* d_in = nullptr;  size_t d_in_bytes = 0;     // staging for host inputs
-    void* d_out = nullptr; size_t d_out_bytes = 0;    // staging for host outputs
-    bool lz4_setup_done = false;   // setup is once-only until destroy (lz4.c:4999-5016)
-    bool lz4_frameless = false;
-    bool snappy_setup_done = false;
-    // pipelined host transfers
-    cudaStream_t up = nullptr, down = nullptr;         // H2D / D2H copy streams
-    uint32_t* d_flag = nullptr;                        // input watermark (device)
-    uint32_t* h_marks = nullptr;                       // pinned source values for the watermark copies
-    cudaEvent_t ev[2 * 64 + 2] = {};
-    bool pipe_ready = false, pipe_failed = false;
-};
-Global g;
-
 constexpr int kMaxPieces = 64;
 constexpr size_t kPipeMinBytes = size_t(8) << 20;      // below this the plain sequence is as fast
 
-bool ensure_pipe() {
-    if (g.pipe_ready) return true;
-    if (g.pipe_failed || getenv("AOCL_GPU_NO_PIPELINE")) return false;
-    bool ok = cudaStreamCreateWithFlags(&g.up, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&g.down, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaMalloc(&g.d_flag, 256) == cudaSuccess &&
-              cudaMallocHost(&g.h_marks, sizeof(uint32_t) * (kMaxPieces + 1)) == cudaSuccess;
-    for (auto& e : g.ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) { cudaGetLastError(); g.pipe_failed = true; return false; }
-    g.pipe_ready = true;
+// Everything one call needs on one GPU: a device context (stream, workspace, result block), two staging
+// buffers and the copy streams / events of the pipelined host transfers.  Calls from different host threads
+// take different HostCtx objects and run concurrently, like the reference (which has no locks on its data
+// path: README.md:332-333); the devices of AOCL_GPU_DEVICES are used round robin.
+struct HostCtx {
+    int device = 0;
+    bool busy = false;
+    aocl_gpu_ctx_t ctx = nullptr;
+    void* d_in = nullptr;  size_t d_in_bytes = 0;     // staging for host inputs
+    void* d_out = nullptr; size_t d_out_bytes = 0;    // staging for host outputs
+    cudaStream_t up = nullptr, down = nullptr;         // H2D / D2H copy streams
+    uint32_t* d_flag = nullptr;                        // input watermark (device)
+    uint32_t* h_marks = nullptr;                       // pinned source values for the watermark copies
+    cudaEvent_t ev[2 * kMaxPieces + 2] = {};
+    bool pipe_ready = false, pipe_failed = false;
+    bool lz4_frameless = false;                        // copied from the process-wide setup state at acquire
+};
+
+struct Global {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool init_done = false, init_failed = false;
+    std::vector<int> devices;          // AOCL_GPU_DEVICES ("0-3", "0,2,5"), else AOCL_GPU_DEVICE, else the current device
+    std::vector<HostCtx*> pool;
+    int per_device = 4;                // AOCL_GPU_CONTEXTS: concurrent calls served per device (more callers wait)
+    unsigned rr = 0;
+    bool lz4_setup_done = false;       // setup is once-only until destroy (lz4.c:4999-5016)
+    bool lz4_frameless = false;
+    bool snappy_setup_done = false;
+};
+Global g;
+
+// The library never leaves the caller's current device changed.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void parse_devices_locked() {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return; }
+    if (const char* e = getenv("AOCL_GPU_DEVICES")) {
+        const char* p = e;
+        while (*p) {
+            char* end = nullptr;
+            long a = strtol(p, &end, 10);
+            if (end == p) break;
+            long b = a;
+            if (*end == '-') { p = end + 1; b = strtol(p, &end, 10); if (end == p) break; }
+            for (long d = a; d <= b; d++) if (d >= 0 && d < count) g.devices.push_back((int)d);
+            p = end;
+            while (*p == ',' || *p == ' ') p++;
+        }
+    }
+    if (g.devices.empty()) {
+        int dev = -1;
+        if (const char* e = getenv("AOCL_GPU_DEVICE")) dev = atoi(e);
+        if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+        if (dev >= 0 && dev < count) g.devices.push_back(dev);
+    }
+    if (const char* e = getenv("AOCL_GPU_CONTEXTS")) { const int v = atoi(e); if (v >= 1 && v <= 64) g.per_device = v; }
+}
+
+// Takes a free context (creating one if its device has fewer than per_device), or waits for one.
+HostCtx* acquire() {
+    std::unique_lock<std::mutex> lock(g.mu);
+    if (!g.init_done) {
+        g.init_done = true;
+        parse_devices_locked();
+        if (g.devices.empty()) {
+            g.init_failed = true;
+            fprintf(stderr, "[aocl-llc-b200] no usable CUDA device: the B200 library has no CPU fallback\n");
+        }
+    }
+    if (g.init_failed) return nullptr;
+    for (;;) {
+        const size_t nd = g.devices.size();
+        // least-loaded device first, round robin among equals
+        int best_dev = -1, best_busy = 1 << 30;
+        HostCtx* best_free = nullptr;
+        for (size_t k = 0; k < nd; k++) {
+            const int dev = g.devices[(g.rr + k) % nd];
+            int busy = 0, total = 0;
+            HostCtx* free_one = nullptr;
+            for (HostCtx* h : g.pool) if (h->device == dev) { total++; if (h->busy) busy++; else if (!free_one) free_one = h; }
+            if ((free_one || total < g.per_device) && busy < best_busy) { best_busy = busy; best_dev = dev; best_free = free_one; }
+        }
+        if (best_dev >= 0) {
+            g.rr++;
+            HostCtx* h = best_free;
+            if (!h) {
+                h = new HostCtx();
+                h->device = best_dev;
+                DeviceGuard guard(best_dev);
+                if (aocl_gpu_ctx_create(&h->ctx, best_dev, nullptr) != 0) {
+                    delete h;
+                    if (g.pool.empty()) {
+                        g.init_failed = true;
+                        fprintf(stderr, "[aocl-llc-b200] no usable CUDA device: the B200 library has no CPU fallback\n");
+                        return nullptr;
+                    }
+                    g.cv.wait(lock);
+                    continue;
+                }
+                g.pool.push_back(h);
+            }
+            h->busy = true;
+            h->lz4_frameless = g.lz4_frameless;
+            return h;
+        }
+        g.cv.wait(lock);
+    }
+}
+void release(HostCtx* h) {
+    { std::lock_guard<std::mutex> lock(g.mu); h->busy = false; }
+    g.cv.notify_one();
+}
+struct Lease {
+    HostCtx* h;
+    Lease() : h(acquire()) {}
+    ~Lease() { if (h) release(h); }
+};
+
+bool ensure_pipe(HostCtx& h) {
+    if (h.pipe_ready) return true;
+    if (h.pipe_failed || getenv("AOCL_GPU_NO_PIPELINE")) return false;
+    bool ok = cudaStreamCreateWithFlags(&h.up, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h.down, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&h.d_flag, 256) == cudaSuccess &&
+              cudaMallocHost(&h.h_marks, sizeof(uint32_t) * (kMaxPieces + 1)) == cudaSuccess;
+    for (auto& e : h.ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); h.pipe_failed = true; return false; }
+    h.pipe_ready = true;
     return true;
 }
 
@@ -73,22 +180,9 @@ bool pinned_host(const void* p) {
 
 uint32_t rd32(const unsigned char* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
-bool ensure_ctx() {
-    if (g.ctx) return true;
-    if (g.ctx_failed) return false;
-    int dev = -1;
-    if (const char* e = getenv("AOCL_GPU_DEVICE")) dev = atoi(e);
-    if (aocl_gpu_ctx_create(&g.ctx, dev, nullptr) != 0) {
-        g.ctx_failed = true;
-        fprintf(stderr, "[aocl-llc-b200] no usable CUDA device: the B200 library has no CPU fallback\n");
-        return false;
-    }
-    return true;
-}
-
-bool grow(void** buf, size_t* have, size_t need) {
+bool grow(HostCtx& h, void** buf, size_t* have, size_t need) {
     if (need <= *have) return true;
-    if (*buf) { cudaStreamSynchronize((cudaStream_t)aocl_gpu_ctx_stream(g.ctx)); cudaFree(*buf); *buf = nullptr; *have = 0; }
+    if (*buf) { cudaStreamSynchronize((cudaStream_t)aocl_gpu_ctx_stream(h.ctx)); cudaFree(*buf); *buf = nullptr; *have = 0; }
     need = (need + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
     if (cudaMalloc(buf, need) != cudaSuccess) { cudaGetLastError(); return false; }
     *have = need;
@@ -111,12 +205,12 @@ uint64_t now_ns() {
 // Enqueue the H2D transfer of a pinned host input on the copy stream in pieces, each followed by a
 // 4-byte copy that raises the encoder's input watermark (include/aocl_llc_gpu.h), and make the
 // compute stream wait only for the watermark reset.  Returns false if this input takes the plain path.
-bool stream_input_up(int codec, const char* in, size_t n, void* d_in, cudaStream_t s) {
-    if (n < kPipeMinBytes || !pinned_host(in) || !ensure_pipe()) return false;
+bool stream_input_up(HostCtx& h, int codec, const char* in, size_t n, void* d_in, cudaStream_t s) {
+    if (n < kPipeMinBytes || !pinned_host(in) || !ensure_pipe(h)) return false;
     const uint32_t T = (uint32_t)aocl_gpu_partition_count(codec, n);
-    if (T < 2 || (codec == LZ4 && g.lz4_frameless)) return false;
-    bool ok = cudaMemsetAsync(g.d_flag, 0, sizeof(uint32_t), g.up) == cudaSuccess &&
-              cudaEventRecord(g.ev[0], g.up) == cudaSuccess && cudaStreamWaitEvent(s, g.ev[0], 0) == cudaSuccess;
+    if (T < 2 || (codec == LZ4 && h.lz4_frameless)) return false;
+    bool ok = cudaMemsetAsync(h.d_flag, 0, sizeof(uint32_t), h.up) == cudaSuccess &&
+              cudaEventRecord(h.ev[0], h.up) == cudaSuccess && cudaStreamWaitEvent(s, h.ev[0], 0) == cudaSuccess;
     int pieces = 0;
     if (codec == LZ4) {
         // stripe j = bytes [j*w, (j+1)*w) of EVERY partition (a 2-D copy, pitch = partition size)
@@ -126,35 +220,35 @@ bool stream_input_up(int codec, const char* in, size_t n, void* d_in, cudaStream
         if (pieces > kMaxPieces) pieces = kMaxPieces;
         for (int j = 0; j < pieces && ok; j++) {
             const size_t lo = (size_t)j * w, width = (j == pieces - 1) ? common - lo : w;
-            ok = cudaMemcpy2DAsync((char*)d_in + lo, common, in + lo, common, width, T, cudaMemcpyHostToDevice, g.up) == cudaSuccess;
+            ok = cudaMemcpy2DAsync((char*)d_in + lo, common, in + lo, common, width, T, cudaMemcpyHostToDevice, h.up) == cudaSuccess;
             if (ok && j == pieces - 1 && n > common * T)     // the last partition's n % T extra bytes
-                ok = cudaMemcpyAsync((char*)d_in + common * T, in + common * T, n - common * T, cudaMemcpyHostToDevice, g.up) == cudaSuccess;
-            g.h_marks[j] = (j == pieces - 1) ? 0xffffffffu : (uint32_t)(lo + width);
-            ok = ok && cudaMemcpyAsync(g.d_flag, &g.h_marks[j], sizeof(uint32_t), cudaMemcpyHostToDevice, g.up) == cudaSuccess;
+                ok = cudaMemcpyAsync((char*)d_in + common * T, in + common * T, n - common * T, cudaMemcpyHostToDevice, h.up) == cudaSuccess;
+            h.h_marks[j] = (j == pieces - 1) ? 0xffffffffu : (uint32_t)(lo + width);
+            ok = ok && cudaMemcpyAsync(h.d_flag, &h.h_marks[j], sizeof(uint32_t), cudaMemcpyHostToDevice, h.up) == cudaSuccess;
         }
     } else {
         const size_t piece = size_t(32) << 20;
         pieces = (int)((n + piece - 1) / piece);
         for (int j = 0; j < pieces && ok; j++) {
             const size_t lo = (size_t)j * piece, len = (j == pieces - 1) ? n - lo : piece;
-            ok = cudaMemcpyAsync((char*)d_in + lo, in + lo, len, cudaMemcpyHostToDevice, g.up) == cudaSuccess;
-            g.h_marks[j] = (j == pieces - 1) ? 0xffffffffu : (uint32_t)(lo + len);
-            ok = ok && cudaMemcpyAsync(g.d_flag, &g.h_marks[j], sizeof(uint32_t), cudaMemcpyHostToDevice, g.up) == cudaSuccess;
+            ok = cudaMemcpyAsync((char*)d_in + lo, in + lo, len, cudaMemcpyHostToDevice, h.up) == cudaSuccess;
+            h.h_marks[j] = (j == pieces - 1) ? 0xffffffffu : (uint32_t)(lo + len);
+            ok = ok && cudaMemcpyAsync(h.d_flag, &h.h_marks[j], sizeof(uint32_t), cudaMemcpyHostToDevice, h.up) == cudaSuccess;
         }
     }
     if (!ok) {                                              // whatever was enqueued must drain before the plain path reuses d_in
         cudaGetLastError();
-        cudaStreamSynchronize(g.up);
+        cudaStreamSynchronize(h.up);
         return false;
     }
-    aocl_gpu_set_input_watermark(g.ctx, g.d_flag);
+    aocl_gpu_set_input_watermark(h.ctx, h.d_flag);
     return true;
 }
 
 // Host-to-host decompress of a well-formed multi-partition RAP stream in slabs.  Returns bytes
 // produced, -1 on failure, or -100 when the stream does not qualify (caller takes the plain path,
 // which also produces the reference's error behaviour for malformed frames).
-int64_t decompress_pipelined(int codec, const char* in, size_t n, char* out, size_t out_size, cudaStream_t s) {
+int64_t decompress_pipelined(HostCtx& h, int codec, const char* in, size_t n, char* out, size_t out_size, cudaStream_t s) {
     const unsigned char* u = (const unsigned char*)in;
     uint64_t magic = 0;
     if (n < kPipeMinBytes || n > 0xffffffffull) return -100;
@@ -162,13 +256,12 @@ int64_t decompress_pipelined(int codec, const char* in, size_t n, char* out, siz
     if (magic != kRapMagic) return -100;
     const uint32_t frame = rd32(u + 8), T = rd32(u + 12);
     if (T < 64 || T > 65536 || frame != 16 + 12 * (uint64_t)T || frame > n) return -100;
-    if (!pinned_host(in) || !pinned_host(out) || !ensure_pipe()) return -100;
+    if (!pinned_host(in) || !pinned_host(out) || !ensure_pipe(h)) return -100;
     // A slab is one wave of the tile decoder (one partition per resident CTA, two CTAs per SM), so the
     // slab decodes cost what the single launch costs; at most 24 slabs.  Entries must be laid out back
     // to back in order.
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h.device);
     uint32_t per = sms > 0 ? 2u * (uint32_t)sms : 256u;
     while ((T + per - 1) / per > 24) per += sms > 0 ? 2u * (uint32_t)sms : 256u;
     const int K = (int)((T + per - 1) / per);
@@ -190,32 +283,32 @@ int64_t decompress_pipelined(int codec, const char* in, size_t n, char* out, siz
         out_end[k] = total;
     }
     if (total > out_size || total == 0) return -100;
-    if (!grow(&g.d_in, &g.d_in_bytes, n) || !grow(&g.d_out, &g.d_out_bytes, total)) return -1;
+    if (!grow(h, &h.d_in, &h.d_in_bytes, n) || !grow(h, &h.d_out, &h.d_out_bytes, total)) return -1;
 
     bool ok = true;
     uint64_t lo = 0;
     for (int k = 0; k < K && ok; k++) {                     // all uploads, in order, on the copy stream
-        ok = cudaMemcpyAsync((char*)g.d_in + lo, in + lo, in_end[k] - lo, cudaMemcpyHostToDevice, g.up) == cudaSuccess &&
-             cudaEventRecord(g.ev[1 + k], g.up) == cudaSuccess;
+        ok = cudaMemcpyAsync((char*)h.d_in + lo, in + lo, in_end[k] - lo, cudaMemcpyHostToDevice, h.up) == cudaSuccess &&
+             cudaEventRecord(h.ev[1 + k], h.up) == cudaSuccess;
         lo = in_end[k];
     }
-    ok = ok && cudaStreamWaitEvent(s, g.ev[1], 0) == cudaSuccess &&
-         aocl_gpu_decompress_open_async(g.ctx, codec, g.d_in, n, out_size) == 0;
+    ok = ok && cudaStreamWaitEvent(s, h.ev[1], 0) == cudaSuccess &&
+         aocl_gpu_decompress_open_async(h.ctx, codec, h.d_in, n, out_size) == 0;
     uint64_t olo = 0;
     for (int k = 0; k < K && ok; k++) {
-        ok = cudaStreamWaitEvent(s, g.ev[1 + k], 0) == cudaSuccess &&
-             aocl_gpu_decompress_slab_async(g.ctx, codec, g.d_in, g.d_out, first[k], first[k + 1] - first[k]) == 0 &&
-             cudaEventRecord(g.ev[1 + kMaxPieces + k], s) == cudaSuccess &&
-             cudaStreamWaitEvent(g.down, g.ev[1 + kMaxPieces + k], 0) == cudaSuccess;
+        ok = cudaStreamWaitEvent(s, h.ev[1 + k], 0) == cudaSuccess &&
+             aocl_gpu_decompress_slab_async(h.ctx, codec, h.d_in, h.d_out, first[k], first[k + 1] - first[k]) == 0 &&
+             cudaEventRecord(h.ev[1 + kMaxPieces + k], s) == cudaSuccess &&
+             cudaStreamWaitEvent(h.down, h.ev[1 + kMaxPieces + k], 0) == cudaSuccess;
         if (ok && out_end[k] > olo)
-            ok = cudaMemcpyAsync(out + olo, (char*)g.d_out + olo, out_end[k] - olo, cudaMemcpyDeviceToHost, g.down) == cudaSuccess;
+            ok = cudaMemcpyAsync(out + olo, (char*)h.d_out + olo, out_end[k] - olo, cudaMemcpyDeviceToHost, h.down) == cudaSuccess;
         olo = out_end[k];
     }
-    if (ok) ok = aocl_gpu_decompress_close_async(g.ctx) == 0;
-    const int64_t r = ok ? aocl_gpu_finish(g.ctx) : -1;
-    cudaStreamSynchronize(g.up);
+    if (ok) ok = aocl_gpu_decompress_close_async(h.ctx) == 0;
+    const int64_t r = ok ? aocl_gpu_finish(h.ctx) : -1;
+    cudaStreamSynchronize(h.up);
     cudaStreamSynchronize(s);
-    const bool down_ok = cudaStreamSynchronize(g.down) == cudaSuccess;
+    const bool down_ok = cudaStreamSynchronize(h.down) == cudaSuccess;
     if (!ok) cudaGetLastError();
     if (r < 0 || !down_ok || (uint64_t)r != total) return -1;
     return r;
@@ -223,10 +316,6 @@ int64_t decompress_pipelined(int codec, const char* in, size_t n, char* out, siz
 
 // Returns bytes produced or a negative codec error (the adapters' CODEC_ERROR).
 int64_t run_codec(bool compress, int codec, char* in, size_t in_size, char* out, size_t out_size) {
-    std::lock_guard<std::mutex> lock(g.mu);
-    if (!ensure_ctx()) return -1;
-    cudaStream_t s = (cudaStream_t)aocl_gpu_ctx_stream(g.ctx);
-
     if (compress) {
         if ((in == nullptr && in_size != 0) || out == nullptr || out_size == 0) return -1;   // lz4.c:2656-2657, snappy.cc:2499
         if (codec == SNAPPY && out_size < 32 + in_size + in_size / 6) return -1;             // api/codec.cpp:262-265
@@ -235,33 +324,41 @@ int64_t run_codec(bool compress, int codec, char* in, size_t in_size, char* out,
         if (out == nullptr && out_size != 0) return -1;
         if (codec == LZ4 && out == nullptr) return -1;
     }
+    Lease lease;                                            // one context for the whole call; other threads take others
+    if (!lease.h) return -1;
+    HostCtx& h = *lease.h;
+    DeviceGuard guard(h.device);                            // allocations, streams and events below belong to h.device
+    cudaStream_t s = (cudaStream_t)aocl_gpu_ctx_stream(h.ctx);
 
     const bool in_dev = in_size ? on_device(in) : true;
     const bool out_dev = on_device(out);
     if (!compress && !in_dev && !out_dev) {
-        const int64_t r = decompress_pipelined(codec, in, in_size, out, out_size, s);
+        const int64_t r = decompress_pipelined(h, codec, in, in_size, out, out_size, s);
         if (r != -100) return r;
     }
-    const void* d_in = in;
-    bool streamed = false;
-    if (in_size && !in_dev) {
-        if (!grow(&g.d_in, &g.d_in_bytes, in_size)) return -1;
-        if (compress) streamed = stream_input_up(codec, in, in_size, g.d_in, s);
-        if (!streamed && cudaMemcpyAsync(g.d_in, in, in_size, cudaMemcpyHostToDevice, s) != cudaSuccess) { cudaGetLastError(); return -1; }
-        d_in = g.d_in;
-    }
-    void* d_out = out;
+    // both staging buffers exist before anything is enqueued: no early return may leave a copy in flight
     size_t stage_cap = out_size;
     if (!out_dev) {
         if (compress) { const size_t b = aocl_gpu_compress_bound(codec, in_size); if (b < stage_cap) stage_cap = b; }
-        if (!grow(&g.d_out, &g.d_out_bytes, stage_cap ? stage_cap : 1)) return -1;
-        d_out = g.d_out;
+        if (!grow(h, &h.d_out, &h.d_out_bytes, stage_cap ? stage_cap : 1)) return -1;
     }
-    aocl_gpu_set_lz4_frameless(g.ctx, g.lz4_frameless ? 1 : 0);
-    if (compress) aocl_gpu_compress_async(g.ctx, codec, d_in, in_size, d_out, out_size);
-    else          aocl_gpu_decompress_async(g.ctx, codec, d_in, in_size, d_out, out_size);
-    const int64_t r = aocl_gpu_finish(g.ctx);
-    if (streamed) cudaStreamSynchronize(g.up);              // nothing of this call may still be in flight
+    if (in_size && !in_dev && !grow(h, &h.d_in, &h.d_in_bytes, in_size)) return -1;
+    const void* d_in = in;
+    bool streamed = false;
+    if (in_size && !in_dev) {
+        if (compress) streamed = stream_input_up(h, codec, in, in_size, h.d_in, s);
+        if (!streamed && cudaMemcpyAsync(h.d_in, in, in_size, cudaMemcpyHostToDevice, s) != cudaSuccess) { cudaGetLastError(); return -1; }
+        d_in = h.d_in;
+    }
+    void* d_out = out_dev ? (void*)out : h.d_out;
+    aocl_gpu_set_lz4_frameless(h.ctx, h.lz4_frameless ? 1 : 0);
+    if (compress) aocl_gpu_compress_async(h.ctx, codec, d_in, in_size, d_out, out_size);
+    else          aocl_gpu_decompress_async(h.ctx, codec, d_in, in_size, d_out, out_size);
+    const int64_t r = aocl_gpu_finish(h.ctx);
+    if (streamed) {                                         // nothing of this call may still be in flight or armed
+        cudaStreamSynchronize(h.up);
+        aocl_gpu_set_input_watermark(h.ctx, nullptr);
+    }
     if (r < 0) return -1;
     if (!out_dev && r > 0) {
         if ((size_t)r > stage_cap) return -1;
@@ -269,6 +366,11 @@ int64_t run_codec(bool compress, int codec, char* in, size_t in_size, char* out,
             cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); return -1; }
     }
     return r;
+}
+
+bool ensure_any_ctx() {
+    Lease lease;
+    return lease.h != nullptr;
 }
 
 bool served(aocl_compression_type t) { return t == LZ4 || t == SNAPPY; }
@@ -311,7 +413,7 @@ extern "C" int32_t aocl_llc_setup(aocl_compression_desc* h, aocl_compression_typ
     if (!h) return ERR_INVALID_INPUT;
     h->optLevel = 4;                                          // utils/utils.cpp:148-172 overwrites the caller's value
     if (!served_decode(codec_type)) return ERR_EXCLUDED_METHOD;   // api/api.cpp:156-162
-    std::lock_guard<std::mutex> lock(g.mu);
+    std::unique_lock<std::mutex> lock(g.mu);
     if (codec_type == LZ4 && !g.lz4_setup_done) {
         // optOff (or AOCL_DISABLE_OPT=ON, utils/utils.cpp:207-219) selects the reference's
         // single-threaded layout: one frame-less LZ4 block (lz4.c:4927-4932)
@@ -321,7 +423,8 @@ extern "C" int32_t aocl_llc_setup(aocl_compression_desc* h, aocl_compression_typ
     }
     if (codec_type == SNAPPY) g.snappy_setup_done = true;
     h->workBuf = nullptr;                                     // the reference returns NULL for both codecs
-    return ensure_ctx() ? 0 : ERR_COMPRESSION_FAILED;
+    lock.unlock();
+    return ensure_any_ctx() ? 0 : ERR_COMPRESSION_FAILED;
 }
 
 extern "C" void aocl_llc_destroy(aocl_compression_desc* h, aocl_compression_type codec_type) {

@@ -62,8 +62,12 @@ def test_setup_return_codes(lib):
     d = llc_b200.AoclDesc()
     assert lib.aocl_llc_setup(C.byref(d), -1) == -4            # ERR_UNSUPPORTED_METHOD, api/api.cpp:133-138
     assert lib.aocl_llc_setup(C.byref(d), 7) == -4
-    for excluded in (1, 2, 3, 5, 6):                            # LZ4HC, LZMA, BZIP2, ZLIB, ZSTD: api/api.cpp:156-162
+    for excluded in (2, 3, 5, 6):                               # LZMA, BZIP2, ZLIB, ZSTD: api/api.cpp:156-162
         assert lib.aocl_llc_setup(C.byref(d), excluded) == -3
+    # LZ4HC is served for decompress (api/codec.h:168): setup behaves like LZ4's (here: no device -> failure, on a
+    # GPU box 0, tests/test_gpu_interop.py), compress is refused as an excluded method
+    assert lib.aocl_llc_setup(C.byref(d), 1) in (0, -2)
+    assert lib.aocl_llc_compress(C.byref(d), 1) == -3
     assert d.workBuf is None
 
 
