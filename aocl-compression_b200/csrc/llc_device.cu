@@ -55,7 +55,7 @@ struct aocl_gpu_ctx_s {
     // per SM in flight), else the tile decoder.  Round 1 also measured a parser warp + lane-per-sequence copier
     // (16-19 ms) and lane parsers + lane-per-sequence copiers against global memory (22 ms); both are gone.
     int decoder_mode = 0;           // 0 auto, 1 warp, 4 tile, 5 rowq
-    uint32_t rowq_min_units = 0;    // AOCL_GPU_ROWQ_MIN_UNITS (default 5 x SMs)
+    uint32_t rowq_min_units = 0;    // AOCL_GPU_ROWQ_MIN_UNITS: auto mode takes the row decoder from this many units on
     bool lz4_frameless = false;
     const uint32_t* in_flag = nullptr;   // one-shot input watermark for the next compress (aocl_gpu_set_input_watermark)
     bool batch_mode = false;        // last enqueue was a batch call (finish() returns -failures)
@@ -137,7 +137,7 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_parts_kernel, 128, 0);
     if (per_sm < 1) per_sm = 1;
     c->decode_blocks = per_sm * c->sm_count;
-    c->rowq_min_units = 5u * (uint32_t)c->sm_count;
+    c->rowq_min_units = 0xffffffffu;                           // measured slower than the tile decoder so far: opt-in
     if (const char* e = getenv("AOCL_GPU_ROWQ_MIN_UNITS")) c->rowq_min_units = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("AOCL_GPU_DECODER"))
         c->decoder_mode = strcmp(e, "rowq") == 0 ? 5 : strcmp(e, "tile") == 0 ? 4 : strcmp(e, "warp") == 0 ? 1 : 0;
