@@ -3,7 +3,9 @@
 #include "llc_kernels.cuh"
 #include "../../include/aocl_llc_gpu.h"
 
+#include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,8 +26,10 @@ static std::atomic<uint64_t> g_launches{0};
 constexpr int kProfSlots = 16;
 constexpr int kStabMax = 11;        // shared-table LZ4 encoder CTAs per SM (16 KiB table + 4 KiB owner bytes each)
 
+struct aocl_gpu_shard_s;
 struct aocl_gpu_ctx_s {
     int device = 0;
+    aocl_gpu_shard_s* shard = nullptr;   // one frame over several GPUs (llc_shard.cuh)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t side = nullptr;    // second stream for kernels that run concurrently with the main one
@@ -153,9 +157,11 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
     return 0;
 }
 
+extern "C" void aocl_gpu_shard_destroy(aocl_gpu_ctx_t c);
 extern "C" void aocl_gpu_ctx_destroy(aocl_gpu_ctx_t c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    aocl_gpu_shard_destroy(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->ws) cudaFree(c->ws);
     if (c->d_res) cudaFree(c->d_res);
@@ -380,19 +386,19 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
                     cudaStreamSetAttribute(c->side, cudaStreamAttributeAccessPolicyWindow, &av);
                 }
                 lz4_encode_parts_gtab_kernel<<<(int)(T < (uint32_t)g_ctas ? T : (uint32_t)g_ctas), 32, 0, c->side>>>(
-                    src, (uint64_t)n, T, scratch, slot, rec, ticket, tables, in_flag, c->d_res);
+                    src, Lz4Range{(uint64_t)n, T, 0u, T}, scratch, slot, rec, ticket, tables, in_flag, c->d_res);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
                 cudaEventRecord(c->ev_join, c->side);
             }
             if (a_grid > 0) {
-                lz4_encode_parts_kernel<<<a_grid, 32, 16384, c->stream>>>(src, (uint64_t)n, T, scratch, slot, rec, ticket, in_flag, c->d_res);
+                lz4_encode_parts_kernel<<<a_grid, 32, 16384, c->stream>>>(src, Lz4Range{(uint64_t)n, T, 0u, T}, scratch, slot, rec, ticket, in_flag, c->d_res);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
             }
             if (g_ctas > 0 && T > (uint32_t)a_grid) cudaStreamWaitEvent(c->stream, c->ev_join, 0);
             prof_end(c, enc_slot);
-            LLC_LAUNCH(lz4_stitch_plan_kernel, 1, 1024, 0, c->stream, scratch, slot, rec, (uint64_t)n, T, dst,
-                       (uint64_t)out_cap, plan, c->d_res);
-            LLC_LAUNCH(lz4_compact_kernel, T, 256, 0, c->stream, src, scratch, slot, rec, plan, dst, c->d_res);
+            LLC_LAUNCH(lz4_stitch_plan_kernel, 1, 1024, 0, c->stream, rec, (uint64_t)n, T, dst, (uint64_t)out_cap, plan, c->d_res);
+            LLC_LAUNCH(lz4_compact_kernel, T, 256, 0, c->stream, src, (uint64_t)0, (const uint8_t*)nullptr, (uint64_t)0, scratch, slot, rec,
+                       plan, 0u, dst, (uint64_t)0, c->d_res);
         }
     } else {
         if (out_cap < 32 + n + n / 6) { c->last_rc = -2; return -2; }   // api/codec.cpp:262-265
@@ -454,7 +460,7 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
         if (g_grid) cudaStreamWaitEvent(c->stream, c->ev_join, 0);
         prof_end(c, enc_slot);
         LLC_LAUNCH(snappy_plan_kernel, 1, 1024, 0, c->stream, g, frag_len, frag_off, dst, (uint64_t)out_cap, c->d_res);
-        if (F) LLC_LAUNCH(snappy_compact_kernel, F, 256, 0, c->stream, scratch, slot, frag_len, frag_off, dst, c->d_res);
+        if (F) LLC_LAUNCH(snappy_compact_kernel, F, 256, 0, c->stream, scratch, slot, frag_len, frag_off, 0u, dst, (uint64_t)0, c->d_res);
     }
     end_call(c);
     return 0;
@@ -528,3 +534,5 @@ extern "C" int32_t aocl_gpu_compress_batch_async(aocl_gpu_ctx_t c, int32_t codec
     end_call(c);
     return 0;
 }
+
+#include "llc_shard.cuh"

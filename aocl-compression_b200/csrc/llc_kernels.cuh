@@ -382,44 +382,68 @@ __global__ void __launch_bounds__(32) encode_pages_kernel(int codec, const uint8
 // LZ4 compress.  Step 1: one warp per RAP partition encodes into its scratch slot.
 // Replaces the `#pragma omp parallel` region of AOCL_LZ4_compress_fast_mt (lz4.c:2684-2731).
 // ------------------------------------------------------------------------------------------
-struct Lz4Rec { uint32_t body_len; uint32_t tail_len; };
+// What the stitch needs to know about a partition.  The first token of the body travels with the sizes, so that the
+// stitch plan can be computed by a GPU that does not hold the body (one frame sharded over several GPUs: the records
+// are the only thing the ranks exchange).
+struct Lz4Rec {
+    uint32_t body_len;     // bytes in the scratch slot (0: the partition is all literals)
+    uint32_t tail_len;     // trailing literals left to the next partition
+    uint32_t first_ll;     // literal length of the first sequence of the body
+    uint32_t skip_tok;     // bytes of its token + length bytes | first token << 16
+};
 
 // Persistent: CTAs (one warp each) draw partitions from a shared ticket.  Two flavours run
 // CONCURRENTLY on two streams: the shared-memory flavour is capped at 14 warps per SM by its
 // 16 KiB table, and leaves most issue slots idle because every warp is a serial dependency chain;
 // the global-memory flavour keeps its table in an L2-resident workspace slice (no shared memory),
 // so its warps fill the remaining warp slots of each SM.  Both produce identical bytes.
-__device__ __forceinline__ void lz4_encode_parts_loop(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
+// The launch covers partitions [p0, p0 + cnt) of the frame; `src` points at the first byte of partition p0 and
+// scratch slot t belongs to partition p0 + t (single GPU: p0 = 0, cnt = T).
+struct Lz4Range { uint64_t n; uint32_t T, p0, cnt; };
+__device__ __forceinline__ void lz4_encode_parts_loop(const uint8_t* __restrict__ src, Lz4Range g,
                                                       uint8_t* scratch, uint64_t slot, Lz4Rec* rec, uint32_t* ticket,
                                                       uint32_t* tab_mem, uint8_t* own, const uint32_t* in_flag, CallResult* res) {
     const int lane = lane_id();
     InGate gate(in_flag, &res->error);                       // watermark: bytes present in every partition
-    const uint64_t common = n / T, left = n % T;             // threads/threads.c:91-97,127-135
+    const uint64_t common = g.n / g.T, left = g.n % g.T;     // threads/threads.c:91-97,127-135
     for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(ticket, 1u);
-        i = __shfl_sync(kFull, i, 0);
-        if (i >= T) break;
-        const uint32_t pn = (uint32_t)(common + (i == T - 1 ? left : 0));
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= g.cnt) break;
+        const uint32_t i = g.p0 + t;
+        const uint32_t pn = (uint32_t)(common + (i == g.T - 1 ? left : 0));
         uint32_t tail = 0;
-        const uint32_t body = lz4_encode_unit(src + common * i, pn, scratch + slot * i, -1, i == T - 1, &tail, tab_mem, own, lane, gate);
-        if (lane == 0) { rec[i].body_len = body; rec[i].tail_len = tail; }
+        uint8_t* const body_at = scratch + slot * t;
+        const uint32_t body = lz4_encode_unit(src + common * t, pn, body_at, -1, i == g.T - 1, &tail, tab_mem, own, lane, gate);
+        __syncwarp();                                        // the body bytes (written by all lanes) are ordered before lane 0's reads
+        if (lane == 0) {
+            Lz4Rec r;
+            r.body_len = body; r.tail_len = tail; r.first_ll = 0; r.skip_tok = 0;
+            if (body) {
+                const uint32_t tok = __ldcg(body_at);
+                uint32_t ll = tok >> 4, skip = 1;
+                if (ll == 15) { uint32_t x; do { x = __ldcg(body_at + skip); skip++; ll += x; } while (x == 255); }
+                r.first_ll = ll; r.skip_tok = skip | (tok << 16);
+            }
+            rec[i] = r;
+        }
         __syncwarp();
     }
 }
-__global__ void __launch_bounds__(32, 28) lz4_encode_parts_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
+__global__ void __launch_bounds__(32, 28) lz4_encode_parts_kernel(const uint8_t* __restrict__ src, Lz4Range g,
                                                               uint8_t* scratch, uint64_t slot, Lz4Rec* rec, uint32_t* ticket,
                                                               const uint32_t* in_flag, CallResult* res) {
     extern __shared__ __align__(16) uint32_t tab_mem[];
     __shared__ uint8_t own_mem[kLeanOwnBytes];
-    lz4_encode_parts_loop(src, n, T, scratch, slot, rec, ticket, tab_mem, own_mem, in_flag, res);
+    lz4_encode_parts_loop(src, g, scratch, slot, rec, ticket, tab_mem, own_mem, in_flag, res);
 }
-__global__ void __launch_bounds__(32, 28) lz4_encode_parts_gtab_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t T,
+__global__ void __launch_bounds__(32, 28) lz4_encode_parts_gtab_kernel(const uint8_t* __restrict__ src, Lz4Range g,
                                                                    uint8_t* scratch, uint64_t slot, Lz4Rec* rec,
                                                                    uint32_t* ticket, uint32_t* tables,
                                                                    const uint32_t* in_flag, CallResult* res) {
     __shared__ uint8_t own_mem[kLeanOwnBytes];
-    lz4_encode_parts_loop(src, n, T, scratch, slot, rec, ticket, tables + (size_t)blockIdx.x * 4096, own_mem, in_flag, res);
+    lz4_encode_parts_loop(src, g, scratch, slot, rec, ticket, tables + (size_t)blockIdx.x * 4096, own_mem, in_flag, res);
 }
 
 // Frame-less block written straight to the destination (T == 1, lz4.c:2674-2677).
@@ -450,8 +474,8 @@ struct Lz4Plan {
     uint64_t carry_src;   // source offset of the inherited literals
 };
 
-__global__ void __launch_bounds__(1024) lz4_stitch_plan_kernel(const uint8_t* __restrict__ scratch, uint64_t slot,
-                                                               const Lz4Rec* __restrict__ rec, uint64_t n, uint32_t T,
+// `dst` == nullptr: plan only (a rank that does not own the head of the stream).
+__global__ void __launch_bounds__(1024) lz4_stitch_plan_kernel(const Lz4Rec* __restrict__ rec, uint64_t n, uint32_t T,
                                                                uint8_t* dst, uint64_t out_cap, Lz4Plan* plan,
                                                                CallResult* res) {
     __shared__ uint64_t sm[40];
@@ -498,10 +522,7 @@ __global__ void __launch_bounds__(1024) lz4_stitch_plan_kernel(const uint8_t* __
             p.out_len = 0; p.skip = 0; p.new_ll = 0; p.token_low = 0;
             carry += r.tail_len;
         } else {
-            const uint8_t* b = scratch + slot * i;
-            const uint32_t tok = b[0];
-            uint32_t ll = tok >> 4, skip = 1;
-            if (ll == 15) { uint32_t x; do { x = b[skip++]; ll += x; } while (x == 255); }
+            const uint32_t tok = r.skip_tok >> 16, skip = r.skip_tok & 0xffffu, ll = r.first_ll;
             const uint32_t nl = ll + carry;
             const uint32_t hdr = 1 + (nl >= 15 ? (nl - 15) / 255 + 1 : 0);
             p.skip = skip; p.new_ll = nl; p.token_low = tok & 15;
@@ -529,7 +550,7 @@ __global__ void __launch_bounds__(1024) lz4_stitch_plan_kernel(const uint8_t* __
         uint32_t dlen;
         if (r.body_len == 0) { dlen = 0; carry += r.tail_len; }
         else { dlen = pn - r.tail_len + carry; carry = r.tail_len; }
-        if (fits) {
+        if (fits && dst) {
             uint8_t* e = dst + kRapHeaderBytes + (uint64_t)kRapEntryBytes * i;
             st_u32_bytes(e, (uint32_t)base); st_u32_bytes(e + 4, olen); st_u32_bytes(e + 8, dlen);
         }
@@ -537,8 +558,10 @@ __global__ void __launch_bounds__(1024) lz4_stitch_plan_kernel(const uint8_t* __
     }
     if (tid == 0) {
         if (fits) {
-            st_u32_bytes(dst, (uint32_t)kRapMagic); st_u32_bytes(dst + 4, (uint32_t)(kRapMagic >> 32));
-            st_u32_bytes(dst + 8, (uint32_t)frame); st_u32_bytes(dst + 12, T);    // threads/threads.c:105-110
+            if (dst) {
+                st_u32_bytes(dst, (uint32_t)kRapMagic); st_u32_bytes(dst + 4, (uint32_t)(kRapMagic >> 32));
+                st_u32_bytes(dst + 8, (uint32_t)frame); st_u32_bytes(dst + 12, T);    // threads/threads.c:105-110
+            }
             res->value = (long long)total;
         } else { res->error = 1; res->value = kErrCorrupt; }
     }
@@ -561,23 +584,58 @@ __device__ inline void block_copy(uint8_t* dst, const uint8_t* src, uint32_t len
     if (done + tid < len) dst[done + tid] = src[done + tid];
 }
 
-// Step 3: compaction.  CTA i writes [re-encoded first token][inherited literals][rest of body i]
-// at its final offset.  Replaces the memcpy chain of lz4.c:2825-2877.
-__global__ void __launch_bounds__(256) lz4_compact_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ scratch,
+// Step 3: compaction.  CTA t writes [re-encoded first token][inherited literals][rest of body] of partition
+// p0 + t at its final offset.  Replaces the memcpy chain of lz4.c:2825-2877.  `src` holds the input from byte
+// `src_off` of the frame on; inherited literals that start before it (the tail of the previous GPU's last
+// partitions) come from `halo`, which holds the `halo_len` input bytes in front of src_off.  The destination
+// `dst` corresponds to stream offset `dst_off`.
+__global__ void __launch_bounds__(256) lz4_compact_kernel(const uint8_t* __restrict__ src, uint64_t src_off,
+                                                          const uint8_t* __restrict__ halo, uint64_t halo_len,
+                                                          const uint8_t* __restrict__ scratch,
                                                           uint64_t slot, const Lz4Rec* __restrict__ rec,
-                                                          const Lz4Plan* __restrict__ plan, uint8_t* dst,
-                                                          const CallResult* res) {
+                                                          const Lz4Plan* __restrict__ plan, uint32_t p0, uint8_t* dst,
+                                                          uint64_t dst_off, const CallResult* res) {
     if (res->error) return;
-    const uint32_t i = blockIdx.x;
+    const uint32_t t = blockIdx.x, i = p0 + t;
     const Lz4Plan p = plan[i];
     if (p.out_len == 0) return;
-    uint8_t* o = dst + p.out_off;
+    uint8_t* o = dst + (p.out_off - dst_off);
     const uint32_t nl = p.new_ll;
     const uint32_t ext = nl >= 15 ? (nl - 15) / 255 + 1 : 0;
     if (threadIdx.x == 0) o[0] = (uint8_t)((min(nl, 15u) << 4) | p.token_low);
     for (uint32_t j = threadIdx.x; j < ext; j += blockDim.x) o[1 + j] = (j + 1 < ext) ? (uint8_t)255 : (uint8_t)((nl - 15) % 255);
-    block_copy(o + 1 + ext, src + p.carry_src, p.carry);
-    block_copy(o + 1 + ext + p.carry, scratch + slot * i + p.skip, rec[i].body_len - p.skip);
+    uint8_t* lit = o + 1 + ext;
+    uint32_t before = 0;                                     // carry bytes that lie in front of this GPU's slice
+    if (p.carry_src < src_off) {
+        before = (uint32_t)min((uint64_t)p.carry, src_off - p.carry_src);
+        block_copy(lit, halo + (halo_len - (src_off - p.carry_src)), before);
+    }
+    block_copy(lit + before, src + (p.carry_src + before - src_off), p.carry - before);
+    block_copy(lit + p.carry, scratch + slot * t + p.skip, rec[i].body_len - p.skip);
+}
+
+// One frame over several GPUs: what a rank learns from the plan -- the byte range of the final stream it writes
+// and how many input bytes in front of its slice its partitions inherit as literals.
+struct ShardInfo { unsigned long long halo, out_lo, out_hi, total; };
+__global__ void __launch_bounds__(256) lz4_shard_info_kernel(const Lz4Plan* __restrict__ plan, uint64_t n, uint32_t T, uint32_t p0,
+                                                             uint32_t cnt, const CallResult* res, ShardInfo* info) {
+    __shared__ unsigned long long s_halo;
+    if (threadIdx.x == 0) s_halo = 0;
+    __syncthreads();
+    const uint64_t common = n / T, src_off = common * p0;
+    unsigned long long h = 0;
+    for (uint32_t t = threadIdx.x; t < cnt; t += blockDim.x) {
+        const Lz4Plan p = plan[p0 + t];
+        if (p.out_len && p.carry_src < src_off) h = max(h, (unsigned long long)(src_off - p.carry_src));
+    }
+    atomicMax(&s_halo, h);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        info->halo = s_halo;
+        info->out_lo = p0 == 0 ? 0ull : plan[p0].out_off;
+        info->out_hi = (unsigned long long)plan[p0 + cnt - 1].out_off + plan[p0 + cnt - 1].out_len;
+        info->total = res->error ? 0ull : (unsigned long long)res->value;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -586,6 +644,7 @@ __global__ void __launch_bounds__(256) lz4_compact_kernel(const uint8_t* __restr
 // ------------------------------------------------------------------------------------------
 struct SnappyGeom {
     uint64_t n; uint32_t T; uint32_t frags_common; uint32_t frags_total; uint64_t common; uint64_t left;
+    uint32_t f0, fcnt; uint64_t src_off;                     // the fragment range a launch works on
 };
 __host__ __device__ inline SnappyGeom snappy_geom(uint64_t n, uint32_t T) {
     SnappyGeom g;
@@ -593,6 +652,7 @@ __host__ __device__ inline SnappyGeom snappy_geom(uint64_t n, uint32_t T) {
     g.frags_common = (uint32_t)((g.common + kSnappyBlock - 1) / kSnappyBlock);
     const uint32_t last = (uint32_t)((g.common + g.left + kSnappyBlock - 1) / kSnappyBlock);
     g.frags_total = (T - 1) * g.frags_common + last;
+    g.f0 = 0; g.fcnt = g.frags_total; g.src_off = 0;
     return g;
 }
 __device__ __forceinline__ void snappy_locate(const SnappyGeom& g, uint32_t f, uint32_t* part, uint64_t* off, uint32_t* len) {
@@ -604,20 +664,23 @@ __device__ __forceinline__ void snappy_locate(const SnappyGeom& g, uint32_t f, u
     *part = p; *off = g.common * p + o; *len = (uint32_t)min((uint64_t)kSnappyBlock, pn - o);
 }
 
+// The launch covers fragments [g.f0, g.f0 + g.fcnt) of the frame; `src` holds the input from byte g.src_off on and
+// scratch slot k belongs to fragment f0 + k (single GPU: f0 = 0, fcnt = frags_total, src_off = 0).
 __device__ __forceinline__ void snappy_encode_frags_loop(const uint8_t* __restrict__ src, const SnappyGeom& g, uint8_t* scratch,
                                                          uint64_t slot, uint32_t* frag_len, uint32_t* ticket, uint16_t* tab,
                                                          uint32_t* claim, const uint32_t* in_flag, CallResult* res) {
     const int lane = lane_id();
     InGate gate(in_flag, &res->error);                       // watermark: bytes present from the start of the input
     for (;;) {
-        uint32_t f = 0;
-        if (lane == 0) f = atomicAdd(ticket, 1u);
-        f = __shfl_sync(kFull, f, 0);
-        if (f >= g.frags_total) break;
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(ticket, 1u);
+        k = __shfl_sync(kFull, k, 0);
+        if (k >= g.fcnt) break;
+        const uint32_t f = g.f0 + k;
         uint32_t part, len; uint64_t off;
         snappy_locate(g, f, &part, &off, &len);
         gate.wait((uint32_t)(off + len));
-        const uint32_t got = snappy_encode_fragment_lean(src + off, len, scratch + slot * f, tab, claim, lane);
+        const uint32_t got = snappy_encode_fragment_lean(src + (off - g.src_off), len, scratch + slot * k, tab, claim, lane);
         if (lane == 0) frag_len[f] = got;
         __syncwarp();
     }
@@ -659,6 +722,7 @@ __global__ void __launch_bounds__(1024) snappy_plan_kernel(SnappyGeom g, const u
     for (uint32_t f = lo; f < hi; f++) { frag_off[f] = base; base += frag_len[f]; }
     __syncthreads();
     if (!fits) { if (tid == 0) { res->error = 1; res->value = kErrCorrupt; } return; }
+    if (!dst) { if (tid == 0) res->value = (long long)total; return; }   // plan only (a rank that does not own the head)
     if (framed) {
         for (uint32_t p = tid; p < g.T; p += blockDim.x) {      // RAP_i = {offset of body_i, |body_i|, part_i}
             const uint32_t f0 = p * g.frags_common;
@@ -683,11 +747,11 @@ __global__ void __launch_bounds__(1024) snappy_plan_kernel(SnappyGeom g, const u
 // Step 3: compaction of the fragment bodies.
 __global__ void __launch_bounds__(256) snappy_compact_kernel(const uint8_t* __restrict__ scratch, uint64_t slot,
                                                              const uint32_t* __restrict__ frag_len,
-                                                             const uint64_t* __restrict__ frag_off, uint8_t* dst,
-                                                             const CallResult* res) {
+                                                             const uint64_t* __restrict__ frag_off, uint32_t f0, uint8_t* dst,
+                                                             uint64_t dst_off, const CallResult* res) {
     if (res->error) return;
-    const uint32_t f = blockIdx.x;
-    block_copy(dst + frag_off[f], scratch + slot * f, frag_len[f]);
+    const uint32_t f = f0 + blockIdx.x;
+    block_copy(dst + (frag_off[f] - dst_off), scratch + slot * blockIdx.x, frag_len[f]);
 }
 
 }  // namespace llc

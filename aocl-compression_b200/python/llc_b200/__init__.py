@@ -14,6 +14,23 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # aocl-compression_b200/
 REPO_ROOT = os.path.dirname(PKG_DIR)
+def shard_unique_id() -> bytes:
+    """128 bytes (an ncclUniqueId) that rank 0 hands to the other ranks before shard_init()."""
+    buf = C.create_string_buffer(128)
+    rc = load().aocl_gpu_shard_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"aocl_gpu_shard_unique_id failed ({rc}): libnccl.so.2 not loadable")
+    return buf.raw
+
+
+def shard_range(codec: int, n: int, rank: int, nranks: int):
+    """-> (first partition, partition count, byte offset, byte length) of a rank's share, or None if n has fewer
+    partitions than ranks."""
+    f, c, o, ln = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+    rc = load().aocl_gpu_shard_range(codec, n, rank, nranks, C.byref(f), C.byref(c), C.byref(o), C.byref(ln))
+    return None if rc != 0 else (f.value, c.value, o.value, ln.value)
+
+
 # AOCL_LLC_LIB points experiments at an A/B build of the same sources (make ... LIB=lib_x); the product is lib/
 LIB_PATH = os.environ.get("AOCL_LLC_LIB") or os.path.join(PKG_DIR, "lib", "libaocl_compression.so")
 
@@ -49,7 +66,9 @@ GPU_API = ["aocl_gpu_ctx_create", "aocl_gpu_ctx_destroy", "aocl_gpu_ctx_stream",
            "aocl_gpu_decompress_range_async", "aocl_gpu_decompress_batch_async", "aocl_gpu_compress_batch_async",
            "aocl_gpu_launch_count", "aocl_gpu_set_profiling", "aocl_gpu_profile_count", "aocl_gpu_profile_get",
            "aocl_gpu_debug_counters", "aocl_gpu_set_input_watermark", "aocl_gpu_decompress_open_async",
-           "aocl_gpu_decompress_slab_async", "aocl_gpu_decompress_close_async"]
+           "aocl_gpu_decompress_slab_async", "aocl_gpu_decompress_close_async",
+           "aocl_gpu_shard_unique_id", "aocl_gpu_shard_init", "aocl_gpu_shard_destroy", "aocl_gpu_shard_range",
+           "aocl_gpu_compress_sharded", "aocl_gpu_decompress_sharded"]
 
 _lib = None
 
@@ -95,6 +114,12 @@ def load() -> C.CDLL:
         "aocl_gpu_decompress_open_async": (i32, [vp, i32, vp, sz, sz]),
         "aocl_gpu_decompress_slab_async": (i32, [vp, i32, vp, vp, u32, u32]),
         "aocl_gpu_decompress_close_async": (i32, [vp]),
+        "aocl_gpu_shard_unique_id": (i32, [vp]),
+        "aocl_gpu_shard_init": (i32, [vp, vp, i32, i32]),
+        "aocl_gpu_shard_destroy": (None, [vp]),
+        "aocl_gpu_shard_range": (i32, [i32, sz, i32, i32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64), C.POINTER(u64)]),
+        "aocl_gpu_compress_sharded": (i64, [vp, i32, vp, sz, vp, sz, C.POINTER(u64), C.POINTER(u64)]),
+        "aocl_gpu_decompress_sharded": (i64, [vp, i32, vp, sz, vp, sz, C.POINTER(u64), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)     # AttributeError here == a declared symbol is not exported
@@ -169,6 +194,25 @@ class GpuContext:
             ms = self.L.aocl_gpu_profile_get(self.h, i, buf, 64)
             out.append((buf.value.decode(), float(ms)))
         return out
+
+    # ---- one frame over several GPUs (include/aocl_llc_gpu.h, "ONE frame over several GPUs")
+    def shard_init(self, id_bytes: bytes, rank: int, nranks: int) -> int:
+        buf = C.create_string_buffer(bytes(id_bytes), 128)
+        return self.L.aocl_gpu_shard_init(self.h, C.cast(buf, C.c_void_p), rank, nranks)
+
+    def compress_sharded(self, codec, src_slice, n_total, dst_slice):
+        """-> (stream length or < 0, offset of this rank's bytes in the stream, their length)"""
+        off, ln = C.c_uint64(0), C.c_uint64(0)
+        r = self.L.aocl_gpu_compress_sharded(self.h, codec, src_slice.data_ptr(), n_total, dst_slice.data_ptr(), dst_slice.numel(),
+                                             C.byref(off), C.byref(ln))
+        return r, off.value, ln.value
+
+    def decompress_sharded(self, codec, stream_base_ptr, n, dst_slice):
+        """stream_base_ptr: device address that the stream's offset 0 maps to.  -> (total or < 0, output offset, length)"""
+        off, ln = C.c_uint64(0), C.c_uint64(0)
+        r = self.L.aocl_gpu_decompress_sharded(self.h, codec, stream_base_ptr, n, dst_slice.data_ptr(), dst_slice.numel(),
+                                               C.byref(off), C.byref(ln))
+        return r, off.value, ln.value
 
     @property
     def stream(self) -> int:

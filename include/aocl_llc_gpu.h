@@ -84,6 +84,33 @@ int32_t aocl_gpu_decompress_range_async(aocl_gpu_ctx_t ctx, int32_t codec, const
                                         void *d_out, size_t out_cap, uint32_t first, uint32_t count,
                                         uint64_t out_origin);
 
+/* ---- ONE frame over several GPUs ------------------------------------------------------------
+ * One process (or host thread) per GPU, each with its own context.  Rank r of R owns the contiguous partition
+ * range [floor(r*T/R), floor((r+1)*T/R)): it holds only that slice of the input, works only on those partitions
+ * and writes only its own byte range of the result.  The library exchanges, over NCCL on the context's stream:
+ * the per-partition records (compress: every rank runs the same stitch plan, rank 0 writes the RAP frame), the
+ * trailing literals a rank's first partitions inherit from its predecessor (LZ4 compress, lz4.c:2808-2877), and
+ * {bytes produced, error} (decompress).  Replaces the OpenMP fork/join + serial stitch of lz4.c:2684-2905,
+ * 4785-4890 and snappy.cc:2506-2655, 2271-2390.  All calls are collective and blocking.
+ *   unique_id : rank 0 obtains 128 bytes (an ncclUniqueId) and hands them to the other ranks by any means;
+ *   init      : joins the communicator on this context's device;
+ *   range     : the partitions and input bytes rank `rank` owns of an n-byte input (-2: fewer partitions than ranks);
+ *   compress  : d_in_slice = input bytes [byte_off, byte_off + byte_len).  On return d_out_slice holds bytes
+ *               [*out_off, *out_off + *out_len) of the final stream (rank 0: from 0, RAP frame first); the return
+ *               value is the length of the whole stream, the same on every rank, or < 0;
+ *   decompress: d_stream addresses the stream by its own offsets; the frame header, the entry table (and Snappy's
+ *               varint) and this rank's partitions must be present.  On return d_out_slice holds output bytes
+ *               [*out_off, *out_off + *out_len); the return value is the total, the same on every rank, or < 0. */
+int32_t aocl_gpu_shard_unique_id(void *id_out_128_bytes);
+int32_t aocl_gpu_shard_init(aocl_gpu_ctx_t ctx, const void *id_128_bytes, int32_t rank, int32_t nranks);
+void aocl_gpu_shard_destroy(aocl_gpu_ctx_t ctx);
+int32_t aocl_gpu_shard_range(int32_t codec, size_t n, int32_t rank, int32_t nranks, uint32_t *first_partition,
+                             uint32_t *partition_count, uint64_t *byte_off, uint64_t *byte_len);
+int64_t aocl_gpu_compress_sharded(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in_slice, size_t n_total,
+                                  void *d_out_slice, size_t out_cap, uint64_t *out_off, uint64_t *out_len);
+int64_t aocl_gpu_decompress_sharded(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_stream, size_t n,
+                                    void *d_out_slice, size_t out_cap, uint64_t *out_off, uint64_t *out_len);
+
 /* Slab-wise decode of one RAP stream, for callers that overlap the decode with their own transfers
  * (aocl_llc_decompress does, for host buffers: H2D of slab k+1 | decode of slab k | D2H of slab k-1).
  *   open : parse + validate the frame at d_in (the header, the entry table and -- Snappy -- the varint
