@@ -61,6 +61,7 @@ struct aocl_gpu_ctx_s {
     int decoder_mode = 0;           // 0 auto, 1 warp, 4 tile, 5 rowq
     uint32_t rowq_min_units = 0;    // AOCL_GPU_ROWQ_MIN_UNITS: auto mode takes the row decoder from this many units on
     bool lz4_frameless = false;
+    bool fastparse = false;         // AOCL_GPU_MODE=fastparse / aocl_gpu_set_mode(): the named non-exact LZ4 RAP encoder
     const uint32_t* in_flag = nullptr;   // one-shot input watermark for the next compress (aocl_gpu_set_input_watermark)
     bool batch_mode = false;        // last enqueue was a batch call (finish() returns -failures)
     int last_rc = 0;                // enqueue-time failure to report from finish()
@@ -127,6 +128,7 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
         if (c->l2_persist_bytes) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_bytes);
         if (getenv("AOCL_GPU_VERBOSE")) fprintf(stderr, "[aocl-llc-b200] L2 persisting max %d B, window max %d B\n", max_persist, max_window);
     }
+    if (const char* e = getenv("AOCL_GPU_MODE")) c->fastparse = strcmp(e, "fastparse") == 0;
     if (const char* e = getenv("AOCL_GPU_GTAB_CTAS")) c->gtab_ctas_per_sm = atoi(e);
     if (const char* e = getenv("AOCL_GPU_SNAPPY_GTAB_CTAS")) c->snappy_gtab_ctas_per_sm = atoi(e);
     if (const char* e = getenv("AOCL_GPU_SNAPPY_STAB_CTAS")) c->snappy_stab_ctas_per_sm = atoi(e);
@@ -176,6 +178,12 @@ extern "C" void aocl_gpu_ctx_destroy(aocl_gpu_ctx_t c) {
 
 extern "C" void* aocl_gpu_ctx_stream(aocl_gpu_ctx_t c) { return c ? (void*)c->stream : nullptr; }
 extern "C" void aocl_gpu_set_lz4_frameless(aocl_gpu_ctx_t c, int32_t on) { if (c) c->lz4_frameless = on != 0; }
+extern "C" int32_t aocl_gpu_set_mode(aocl_gpu_ctx_t c, const char* mode) {
+    if (!c || !mode) return -5;
+    if (strcmp(mode, "exact") == 0) { c->fastparse = false; return 0; }
+    if (strcmp(mode, "fastparse") == 0) { c->fastparse = true; return 0; }
+    return -4;
+}
 extern "C" void aocl_gpu_set_input_watermark(aocl_gpu_ctx_t c, const uint32_t* d_flag) { if (c) c->in_flag = d_flag; }
 extern "C" uint64_t aocl_gpu_launch_count(void) { return g_launches.load(); }
 extern "C" void aocl_gpu_set_profiling(aocl_gpu_ctx_t c, int32_t on) { if (c) c->prof = on != 0; }
@@ -386,12 +394,12 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
                     cudaStreamSetAttribute(c->side, cudaStreamAttributeAccessPolicyWindow, &av);
                 }
                 lz4_encode_parts_gtab_kernel<<<(int)(T < (uint32_t)g_ctas ? T : (uint32_t)g_ctas), 32, 0, c->side>>>(
-                    src, Lz4Range{(uint64_t)n, T, 0u, T}, scratch, slot, rec, ticket, tables, in_flag, c->d_res);
+                    src, Lz4Range{(uint64_t)n, T, 0u, T, c->fastparse ? 1u : 0u}, scratch, slot, rec, ticket, tables, in_flag, c->d_res);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
                 cudaEventRecord(c->ev_join, c->side);
             }
             if (a_grid > 0) {
-                lz4_encode_parts_kernel<<<a_grid, 32, 16384, c->stream>>>(src, Lz4Range{(uint64_t)n, T, 0u, T}, scratch, slot, rec, ticket, in_flag, c->d_res);
+                lz4_encode_parts_kernel<<<a_grid, 32, 16384, c->stream>>>(src, Lz4Range{(uint64_t)n, T, 0u, T, c->fastparse ? 1u : 0u}, scratch, slot, rec, ticket, in_flag, c->d_res);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
             }
             if (g_ctas > 0 && T > (uint32_t)a_grid) cudaStreamWaitEvent(c->stream, c->ev_join, 0);

@@ -4,6 +4,7 @@
 #include "llc_common.cuh"
 #include "lz4_codec.cuh"
 #include "lz4_encode_lean.cuh"
+#include "lz4_fastparse.cuh"
 #include "snappy_encode_lean.cuh"
 #include "snappy_codec.cuh"
 #include "lz4_decode_ring.cuh"
@@ -399,7 +400,7 @@ struct Lz4Rec {
 // so its warps fill the remaining warp slots of each SM.  Both produce identical bytes.
 // The launch covers partitions [p0, p0 + cnt) of the frame; `src` points at the first byte of partition p0 and
 // scratch slot t belongs to partition p0 + t (single GPU: p0 = 0, cnt = T).
-struct Lz4Range { uint64_t n; uint32_t T, p0, cnt; };
+struct Lz4Range { uint64_t n; uint32_t T, p0, cnt; uint32_t fastparse; };   // fastparse != 0: the named non-exact mode (lz4_fastparse.cuh)
 __device__ __forceinline__ void lz4_encode_parts_loop(const uint8_t* __restrict__ src, Lz4Range g,
                                                       uint8_t* scratch, uint64_t slot, Lz4Rec* rec, uint32_t* ticket,
                                                       uint32_t* tab_mem, uint8_t* own, const uint32_t* in_flag, CallResult* res) {
@@ -415,7 +416,8 @@ __device__ __forceinline__ void lz4_encode_parts_loop(const uint8_t* __restrict_
         const uint32_t pn = (uint32_t)(common + (i == g.T - 1 ? left : 0));
         uint32_t tail = 0;
         uint8_t* const body_at = scratch + slot * t;
-        const uint32_t body = lz4_encode_unit(src + common * t, pn, body_at, -1, i == g.T - 1, &tail, tab_mem, own, lane, gate);
+        const uint32_t body = g.fastparse ? lz4_fastparse_unit(src + common * t, pn, body_at, i == g.T - 1, &tail, tab_mem, lane, gate)
+                                          : lz4_encode_unit(src + common * t, pn, body_at, -1, i == g.T - 1, &tail, tab_mem, own, lane, gate);
         __syncwarp();                                        // the body bytes (written by all lanes) are ordered before lane 0's reads
         if (lane == 0) {
             Lz4Rec r;

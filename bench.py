@@ -433,6 +433,31 @@ def round_trip(env, args, wl, workload_key, with_cpu, want_identity):
     dec_name = max((k for k in kern if "decode_parts" in k), key=lambda k: kern[k], default="decode_parts_kernel")
     dec_ms = kern.get(dec_name, td)
 
+    # ---- the separately named fastparse mode (LZ4 only): speed and ratio delta, never part of `value`
+    fast = None
+    if codec == LZ4 and env.world == 1:
+        assert ctx.set_mode("fastparse") == 0
+        try:
+            fe = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(3)]
+            fsz = 0
+            for k in range(4):
+                if k:
+                    fe[k - 1][0].record(stream)
+                ctx.compress_async(codec, d_in, d_comp)
+                if k:
+                    fe[k - 1][1].record(stream)
+                fsz = ctx.finish()
+                assert fsz > 0, fsz
+            fms = min(a.elapsed_time(b) for a, b in fe)
+            assert ctx.decompress(codec, d_comp, fsz, d_back) == U and torch.equal(d_back, d_in), "fastparse round trip mismatch"
+            fast = {"mode": "fastparse (AOCL_GPU_MODE=fastparse; never the default)", "compress_ms": fms, "compress_GBps": U / fms / 1e6,
+                    "ratio": fsz / U, "ratio_exact": csz / U, "ratio_delta_vs_exact_pct": 100.0 * (fsz - csz) / csz,
+                    "speedup_vs_exact": tc / fms, "decodes_bit_exact": True}
+        finally:
+            ctx.set_mode("exact")
+        ctx.compress_async(codec, d_in, d_comp)              # the exact stream again, for the checks below
+        assert ctx.finish() == csz
+
     # ---- is the stream the reference's stream?  (outside the timed region; rank 0, N = 1)
     identity = None
     R = load_reference() if (env.rank == 0 and env.world == 1 and (with_cpu or want_identity)) else None
@@ -487,6 +512,8 @@ def round_trip(env, args, wl, workload_key, with_cpu, want_identity):
               "kernels_ms": {k: round(v, 4) for k, v in kern.items()}}
     if identity:
         detail.update(identity)
+    if fast:
+        detail["fastparse"] = fast
     if per_rank:
         detail["per_rank"] = per_rank
     return {

@@ -64,6 +64,15 @@ int64_t aocl_gpu_decompress(aocl_gpu_ctx_t ctx, int32_t codec, const void *d_in,
  * optOff=1 or one OpenMP thread): 1 = on, 0 = off (default). */
 void aocl_gpu_set_lz4_frameless(aocl_gpu_ctx_t ctx, int32_t on);
 
+/* Compress mode of LZ4 RAP frames (env AOCL_GPU_MODE at context creation, or this call):
+ *   "exact"     (default) byte-identical to the reference's LZ4_compress_fast at acceleration 1 (lz4.c:1853-2350);
+ *   "fastparse" the separately named position-parallel parse (csrc/lz4_fastparse.cuh): a valid RAP stream that every
+ *               LZ4 decoder reads, NOT byte-identical to the reference's and with a somewhat larger output; bench.py
+ *               reports its speed and its ratio delta.  Never selected implicitly.  Frame-less blocks (T == 1), Snappy
+ *               and the page batches always use the exact encoders.
+ * Returns 0, -4 for an unknown mode. */
+int32_t aocl_gpu_set_mode(aocl_gpu_ctx_t ctx, const char *mode);
+
 /* Streaming input for the NEXT aocl_gpu_compress_async on this context (one-shot).  d_flag points to a
  * 32-bit watermark in device memory that the caller raises (e.g. with 4-byte H2D copies ordered after
  * the payload copies on its own copy stream) while the encoder is already running:
