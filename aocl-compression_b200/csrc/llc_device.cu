@@ -358,6 +358,7 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
             const uint64_t pmax = n / T + n % T;
             const uint64_t slot = align_up(pmax + pmax / 255 + 32, 256);
             int stab = c->stab_ctas_per_sm, gtab = c->gtab_ctas_per_sm;
+            if (c->fastparse) { stab = 0; if (gtab <= 0) gtab = 32; }      // one flavour: tables in L2, every partition resident
             if (stab < 0 && gtab < 0) {                        // auto: one wave if at all possible
                 if (T <= (uint32_t)c->sm_count * (uint32_t)kStabMax) { stab = kStabMax; gtab = 0; } else { stab = 0; gtab = 32; }
             }
@@ -377,7 +378,7 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
             cudaMemsetAsync(ticket, 0, sizeof(uint32_t), c->stream);
             const uint32_t a_cap = (uint32_t)c->sm_count * (uint32_t)stab;
             const int a_grid = (int)(T < a_cap ? T : a_cap);
-            const int enc_slot = prof_begin(c, "lz4_encode_parts_kernel");   // brackets both flavours (fork .. join)
+            const int enc_slot = prof_begin(c, c->fastparse ? "lz4_fastparse_parts_kernel" : "lz4_encode_parts_kernel");   // brackets both flavours (fork .. join)
             if (g_ctas > 0 && T > (uint32_t)a_grid) {
                 // fork: the global-table flavour shares the ticket and fills the idle warp slots
                 cudaEventRecord(c->ev_fork, c->stream);
@@ -393,13 +394,17 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
                     av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
                     cudaStreamSetAttribute(c->side, cudaStreamAttributeAccessPolicyWindow, &av);
                 }
-                lz4_encode_parts_gtab_kernel<<<(int)(T < (uint32_t)g_ctas ? T : (uint32_t)g_ctas), 32, 0, c->side>>>(
-                    src, Lz4Range{(uint64_t)n, T, 0u, T, c->fastparse ? 1u : 0u}, scratch, slot, rec, ticket, tables, in_flag, c->d_res);
+                if (c->fastparse)
+                    lz4_fastparse_parts_kernel<<<(int)(T < (uint32_t)g_ctas ? T : (uint32_t)g_ctas), 32, 0, c->side>>>(
+                        src, Lz4Range{(uint64_t)n, T, 0u, T}, scratch, slot, rec, ticket, tables, in_flag, c->d_res);
+                else
+                    lz4_encode_parts_gtab_kernel<<<(int)(T < (uint32_t)g_ctas ? T : (uint32_t)g_ctas), 32, 0, c->side>>>(
+                        src, Lz4Range{(uint64_t)n, T, 0u, T}, scratch, slot, rec, ticket, tables, in_flag, c->d_res);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
                 cudaEventRecord(c->ev_join, c->side);
             }
             if (a_grid > 0) {
-                lz4_encode_parts_kernel<<<a_grid, 32, 16384, c->stream>>>(src, Lz4Range{(uint64_t)n, T, 0u, T, c->fastparse ? 1u : 0u}, scratch, slot, rec, ticket, in_flag, c->d_res);
+                lz4_encode_parts_kernel<<<a_grid, 32, 16384, c->stream>>>(src, Lz4Range{(uint64_t)n, T, 0u, T}, scratch, slot, rec, ticket, in_flag, c->d_res);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
             }
             if (g_ctas > 0 && T > (uint32_t)a_grid) cudaStreamWaitEvent(c->stream, c->ev_join, 0);

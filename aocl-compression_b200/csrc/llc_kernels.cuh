@@ -400,7 +400,8 @@ struct Lz4Rec {
 // so its warps fill the remaining warp slots of each SM.  Both produce identical bytes.
 // The launch covers partitions [p0, p0 + cnt) of the frame; `src` points at the first byte of partition p0 and
 // scratch slot t belongs to partition p0 + t (single GPU: p0 = 0, cnt = T).
-struct Lz4Range { uint64_t n; uint32_t T, p0, cnt; uint32_t fastparse; };   // fastparse != 0: the named non-exact mode (lz4_fastparse.cuh)
+struct Lz4Range { uint64_t n; uint32_t T, p0, cnt; };
+template <bool FAST>
 __device__ __forceinline__ void lz4_encode_parts_loop(const uint8_t* __restrict__ src, Lz4Range g,
                                                       uint8_t* scratch, uint64_t slot, Lz4Rec* rec, uint32_t* ticket,
                                                       uint32_t* tab_mem, uint8_t* own, const uint32_t* in_flag, CallResult* res) {
@@ -416,8 +417,8 @@ __device__ __forceinline__ void lz4_encode_parts_loop(const uint8_t* __restrict_
         const uint32_t pn = (uint32_t)(common + (i == g.T - 1 ? left : 0));
         uint32_t tail = 0;
         uint8_t* const body_at = scratch + slot * t;
-        const uint32_t body = g.fastparse ? lz4_fastparse_unit(src + common * t, pn, body_at, i == g.T - 1, &tail, tab_mem, lane, gate)
-                                          : lz4_encode_unit(src + common * t, pn, body_at, -1, i == g.T - 1, &tail, tab_mem, own, lane, gate);
+        const uint32_t body = FAST ? lz4_fastparse_unit(src + common * t, pn, body_at, i == g.T - 1, &tail, tab_mem, lane, gate)
+                                   : lz4_encode_unit(src + common * t, pn, body_at, -1, i == g.T - 1, &tail, tab_mem, own, lane, gate);
         __syncwarp();                                        // the body bytes (written by all lanes) are ordered before lane 0's reads
         if (lane == 0) {
             Lz4Rec r;
@@ -438,14 +439,22 @@ __global__ void __launch_bounds__(32, 28) lz4_encode_parts_kernel(const uint8_t*
                                                               const uint32_t* in_flag, CallResult* res) {
     extern __shared__ __align__(16) uint32_t tab_mem[];
     __shared__ uint8_t own_mem[kLeanOwnBytes];
-    lz4_encode_parts_loop(src, g, scratch, slot, rec, ticket, tab_mem, own_mem, in_flag, res);
+    lz4_encode_parts_loop<false>(src, g, scratch, slot, rec, ticket, tab_mem, own_mem, in_flag, res);
 }
 __global__ void __launch_bounds__(32, 28) lz4_encode_parts_gtab_kernel(const uint8_t* __restrict__ src, Lz4Range g,
                                                                    uint8_t* scratch, uint64_t slot, Lz4Rec* rec,
                                                                    uint32_t* ticket, uint32_t* tables,
                                                                    const uint32_t* in_flag, CallResult* res) {
     __shared__ uint8_t own_mem[kLeanOwnBytes];
-    lz4_encode_parts_loop(src, g, scratch, slot, rec, ticket, tables + (size_t)blockIdx.x * 4096, own_mem, in_flag, res);
+    lz4_encode_parts_loop<false>(src, g, scratch, slot, rec, ticket, tables + (size_t)blockIdx.x * 4096, own_mem, in_flag, res);
+}
+// The named fastparse mode (lz4_fastparse.cuh): same units, same records, same stitch; the tables live in an
+// L2-resident workspace slice so that every partition of a 1 GiB frame is resident at once (the parse is latency bound).
+__global__ void __launch_bounds__(32, 28) lz4_fastparse_parts_kernel(const uint8_t* __restrict__ src, Lz4Range g,
+                                                                 uint8_t* scratch, uint64_t slot, Lz4Rec* rec,
+                                                                 uint32_t* ticket, uint32_t* tables,
+                                                                 const uint32_t* in_flag, CallResult* res) {
+    lz4_encode_parts_loop<true>(src, g, scratch, slot, rec, ticket, tables + (size_t)blockIdx.x * 4096, nullptr, in_flag, res);
 }
 
 // Frame-less block written straight to the destination (T == 1, lz4.c:2674-2677).

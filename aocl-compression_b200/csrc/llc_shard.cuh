@@ -167,7 +167,7 @@ extern "C" int64_t aocl_gpu_compress_sharded(aocl_gpu_ctx_t c, int32_t codec, co
         uint32_t* tables = reinterpret_cast<uint32_t*>(c->ws + o_tab);
         uint8_t* scratch = c->ws + o_scr;
         cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
-        const Lz4Range g{(uint64_t)n, T, p0, cnt, c->fastparse ? 1u : 0u};
+        const Lz4Range g{(uint64_t)n, T, p0, cnt};
         if (stab) LLC_LAUNCH(lz4_encode_parts_kernel, grid, 32, 16384, st, src, g, scratch, slot, rec, ticket, (const uint32_t*)nullptr, c->d_res);
         else LLC_LAUNCH(lz4_encode_parts_gtab_kernel, grid, 32, 0, st, src, g, scratch, slot, rec, ticket, tables, (const uint32_t*)nullptr, c->d_res);
         // all-gather (in place, ranges differ by at most one partition) of the partition records

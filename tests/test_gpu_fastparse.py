@@ -52,7 +52,7 @@ def test_fastparse_streams_decode_everywhere(oracle, ref):
                 assert r == n and back == data.tobytes(), (name, "reference decoder")
             assert ctx.decompress(kat.LZ4, d_comp, c1, d_back) == n and torch.equal(d_back, d_in), (name, "GPU decoder")
             print(f"\n[fastparse] {name:>12}: exact {exact / n:.4f}  fastparse {c1 / n:.4f}  delta {100.0 * (c1 - exact) / exact:+.2f} %")
-            assert c1 <= exact * 1.25 + 4096, (name, exact, c1)
+            assert c1 <= exact * 1.35 + 4096, (name, exact, c1)
         assert ctx.set_mode("exact") == 0 and ctx.set_mode("nonsense") == -4
     finally:
         ctx.close()
