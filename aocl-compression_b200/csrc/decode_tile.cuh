@@ -210,6 +210,7 @@ __device__ __forceinline__ void tile_slow_literals(TileShared<Fmt>& sh, TileStat
         for (uint32_t j = threadIdx.x; j < n; j += kTThreads) sh.ring[(d + j) & kTRingMask] = st.gin[p + done + j];
         __syncthreads();
         tile_flush(sh, st, d + n, false);
+        __syncthreads();                                             // the next piece reuses ring slots the flush may still be reading
     }
     st.op += ll;
 }
@@ -573,22 +574,9 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
             }
         }
     } else {
-        // LLC_T_SRC_WARPS (experiment, default off): run this step on the first W warps only.  The tile model
-        // (tests/tile_model.py) predicts fewer and cheaper jump rounds when fewer rows run side by side, because
-        // more sources are already written when a byte looks at them (text: 16 warps 2.73 rounds / 0.30 jump
-        // visits per byte, 8 warps 2.32 / 0.20, 4 warps 2.03 / 0.12); every thread then collects its unresolved
-        // bytes from P.
-#if defined(LLC_T_SRC_WARPS) && LLC_T_SRC_WARPS < 16
-        constexpr uint32_t kSrcWarps = LLC_T_SRC_WARPS;
-#else
-        constexpr uint32_t kSrcWarps = kTWarps;
-#endif
         const uint32_t le_mask = (2u << lane) - 2u;                  // bits 1 .. lane
         uint32_t bit = 1u;
-#if defined(LLC_T_SRC_WARPS) && LLC_T_SRC_WARPS < 16
-        if (warp < kSrcWarps)
-#endif
-        for (uint32_t row = warp; row < nrows; row += kSrcWarps, bit <<= 1) {
+        for (uint32_t row = warp; row < nrows; row += kTWarps, bit <<= 1) {
             const uint32_t x = (row << 5) + lane;
             const bool live = x >= a0 && x < gend;
             uint32_t k = (uint32_t)sh.row2seq[row] + (uint32_t)__popc(sh.startbits[row] & le_mask) - 1u;
@@ -607,18 +595,8 @@ __device__ __forceinline__ int tile_group(TileShared<Fmt>& sh, TileState& st, ui
             if (e == 0) e = kTPtr | p;
             if (!in_group) e = kTKnown | v;
             if (live) sh.P[x] = (uint16_t)e;
-#if !(defined(LLC_T_SRC_WARPS) && LLC_T_SRC_WARPS < 16)
             if (live && e < kTKnown) unres |= bit;
         }
-#else
-        }
-        __syncthreads();
-        bit = 1u;
-        for (uint32_t row = warp; row < nrows; row += kTWarps, bit <<= 1) {
-            const uint32_t x = (row << 5) + lane;
-            if (x >= a0 && x < gend && sh.P[x] < kTKnown) unres |= bit;
-        }
-#endif
     }
     TP(5);
 

@@ -499,6 +499,25 @@ def round_trip(env, args, wl, workload_key, with_cpu, want_identity):
            "api": "aocl_llc_compress + aocl_llc_decompress, pinned host buffers; transfers pipelined with the kernels "
                   "(striped H2D behind an input watermark / slab-wise H2D-decode-D2H)"}
 
+    # ---- what the box's PCIe / host memory can do for this step's traffic: every rank moves U up and U down with
+    #      plain pinned copies at the same time (aggregate = what N concurrent e2e calls could get at best)
+    pc = torch.empty(U, dtype=torch.uint8, device="cuda")
+    ph = torch.empty(U, dtype=torch.uint8).pin_memory()
+    pe = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    best_up = best_dn = 1e30
+    for _ in range(3):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        pe[0].record(); pc.copy_(ph, non_blocking=True); pe[1].record(); ph.copy_(pc, non_blocking=True); pe[2].record()
+        torch.cuda.synchronize()
+        best_up, best_dn = min(best_up, pe[0].elapsed_time(pe[1])), min(best_dn, pe[1].elapsed_time(pe[2]))
+    up_ms, dn_ms = env.max_over_ranks([best_up, best_dn])
+    floor_ms = (U + csz) / U * up_ms + (U + csz) / U * dn_ms   # this step's H2D and D2H bytes at those rates, nothing overlapped
+    e2e["pcie"] = {"h2d_GBps_aggregate": env.world * U / up_ms / 1e6, "d2h_GBps_aggregate": env.world * U / dn_ms / 1e6,
+                   "transfer_floor_ms_per_step": floor_ms, "frac_of_transfer_floor": floor_ms / (e2e_s * 1e3),
+                   "note": "measured with concurrent plain pinned copies of 1 GiB per rank; a step cannot be faster than its transfers"}
+    del pc, ph
     cpu_baseline = cpu_baseline_sweep(R, data, codec) if (R is not None and with_cpu) else None
     del h_comp, h_back, d_in, d_comp, d_back, h_in
     torch.cuda.empty_cache()
@@ -529,6 +548,66 @@ def round_trip(env, args, wl, workload_key, with_cpu, want_identity):
         "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
+
+
+def sharded_frame(env, args, wl):
+    """N > 1: ONE frame over all the ranks, through the library (aocl_gpu_compress_sharded / _decompress_sharded,
+    csrc/llc_shard.cuh): rank r holds only its slice of the input, the library all-gathers the per-partition records
+    over NCCL, forwards the boundary literals and every rank writes its own byte range of the stream.  Strong
+    scaling of a single frame: the exact LZ4 encoder is one serial chain per partition, so its time barely moves --
+    this is reported next to the frames-x-N headline, not instead of it.  Wall clock around the blocking collective
+    calls (barrier before, device synchronised after), max over ranks."""
+    torch, L, ctx, dist, llc = env.torch, env.L, env.ctx, env.dist, env.llc
+    codec, U = wl["codec"], wl["size"]
+    rng = llc.shard_range(codec, U, env.rank, env.world)
+    if rng is None:
+        return None
+    first, count, boff, blen = rng
+    data = make_data(wl["gen"], U, wl["seed"])               # the same frame on every rank; each keeps its slice
+    box = [llc.shard_unique_id() if env.rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    assert ctx.shard_init(box[0], env.rank, env.world) == 0
+    d_full = torch.from_numpy(data).cuda()
+    cap = L.aocl_gpu_compress_bound(codec, U)
+    d_ref = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ref_len = ctx.compress(codec, d_full, d_ref)             # the single-GPU stream, to compare the pieces with
+    assert ref_len > 0
+    d_slice = d_full[boff:boff + blen].clone()
+    del d_full
+    d_piece = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(blen + (1 << 20), dtype=torch.uint8, device="cuda")
+    tc, td = [], []
+    same = back = True
+    for it in range(4):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        total, off, ln = ctx.compress_sharded(codec, d_slice, U, d_piece)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        assert total == ref_len, (total, ref_len)
+        same = same and bool(torch.equal(d_piece[:ln], d_ref[off:off + ln]))
+        torch.cuda.synchronize(); dist.barrier()
+        t2 = time.perf_counter()
+        tot2, ooff, olen = ctx.decompress_sharded(codec, d_ref.data_ptr(), ref_len, d_out)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        assert tot2 == U, tot2
+        back = back and bool(d_out[:olen].cpu().numpy().tobytes() == data[ooff:ooff + olen].tobytes()) if it == 0 else back
+        if it:
+            tc.append((t1 - t0) * 1e3); td.append((t3 - t2) * 1e3)
+    cms, dms = env.max_over_ranks([min(tc), min(td)])
+    flags = [None] * env.world
+    dist.all_gather_object(flags, (same, back, first, count))
+    del d_ref, d_piece, d_out, d_slice
+    torch.cuda.empty_cache()
+    return {"workload": f"ONE {U >> 20} MiB frame over {env.world} GPUs through aocl_gpu_compress_sharded / aocl_gpu_decompress_sharded "
+                        f"({wl['name'].split(',')[0]})", "n_gpus": env.world, "scaling": "strong",
+            "partitions_per_rank": [f[3] for f in flags],
+            "compress_ms": cms, "decompress_ms": dms, "compress_GBps": U / cms / 1e6, "decompress_GBps": U / dms / 1e6,
+            "pieces_identical_to_the_single_gpu_stream": all(f[0] for f in flags), "slices_round_trip": all(f[1] for f in flags),
+            "collectives": "NCCL inside the library: all-gather of the per-partition records (+ point-to-point boundary literals for LZ4) "
+                           "in compress, all-gather of {bytes, error} in decompress; inside the timed calls"}
 
 
 def frame_variants(env, base, count):
@@ -707,6 +786,8 @@ def run_b200(args, wl):
                 return None
             return {k: r[k] for k in ("value", "unit", "ms_per_step", "config", "detail", "roofline", "roofline_decompress", "cpu_baseline", "e2e")}
         guarded("2_snappy_log_1GiB", snappy_line)
+    if env.world > 1 and args.configs != "none":
+        guarded("1b_one_frame_sharded_over_the_ranks", lambda: sharded_frame(env, args, wl))
     if "3" in want:
         guarded("3_lz4_16_frames_decode", lambda: config3_frames(env, args))
     if "4" in want:

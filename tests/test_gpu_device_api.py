@@ -193,3 +193,50 @@ def test_decode_is_deterministic_under_repetition(torch_mod, ctx, oracle, codec)
             torch.cuda.synchronize()
             assert ctx.decompress(codec, d_comp, len(comp), d_back) == len(data), (name, it)
             assert torch.equal(d_back, d_in), (name, it)
+
+
+@pytest.mark.parametrize("codec", [kat.LZ4, kat.SNAPPY])
+def test_ranged_decode_respects_the_callers_buffer(torch_mod, ctx, oracle, codec):
+    """aocl_gpu_decompress_range_async (the sharding entry point) trusts neither the RAP entries nor the caller's
+    arithmetic: a range that does not fit [d_out, d_out + out_cap) once shifted by out_origin fails BEFORE anything is
+    decoded, and the bytes around the buffer stay untouched."""
+    torch = torch_mod
+    from llc_b200 import shard
+    data = kat.make_input("text", 6 * 262272 + 999)
+    comp = oracle.compress(data, codec)
+    frame, entries = shard.parse_frame(np.frombuffer(comp, dtype=np.uint8))
+    T = len(entries)
+    assert T >= 4
+    origins = shard.output_origins(entries)
+    d_comp = dev(torch, np.frombuffer(comp, dtype=np.uint8))
+    first, count = 2, 2
+    lo = int(origins[first]); hi = int(origins[first + count]) if first + count < T else len(data)
+    need = hi - lo
+    guard = 4096
+    buf = torch.full((guard + need + guard,), 0x5A, dtype=torch.uint8, device="cuda")
+    out = buf[guard:guard + need]
+    torch.cuda.synchronize()
+    ctx.decompress_range_async(codec, d_comp, len(comp), out, first, count, lo)
+    assert ctx.finish() == need
+    assert out.cpu().numpy().tobytes() == data[lo:hi].tobytes()
+    assert bool((buf[:guard] == 0x5A).all()) and bool((buf[guard + need:] == 0x5A).all())
+    for what, o, origin in (("capacity one byte short", buf[guard:guard + need - 1], lo),
+                            ("origin too late (first partition would start before the buffer)", out, lo + 1),
+                            ("origin too early (range would end past the buffer)", out, lo - 1 if lo else 0)):
+        buf.fill_(0x5A)
+        torch.cuda.synchronize()
+        ctx.decompress_range_async(codec, d_comp, len(comp), o, first, count, origin)
+        r = ctx.finish()
+        if what.startswith("origin too early") and lo == 0:
+            continue
+        assert r < 0, what
+        assert bool((buf == 0x5A).all()), what + ": wrote although the range was refused"
+    # a hostile entry table: partition `first` claims a huge decomp_len
+    bad = bytearray(comp)
+    bad[16 + 12 * first + 8: 16 + 12 * first + 12] = (0x7fffffff).to_bytes(4, "little")
+    d_bad = dev(torch, np.frombuffer(bytes(bad), dtype=np.uint8))
+    buf.fill_(0x5A)
+    torch.cuda.synchronize()
+    ctx.decompress_range_async(codec, d_bad, len(bad), out, first, count, lo)
+    assert ctx.finish() < 0
+    assert bool((buf == 0x5A).all())
