@@ -23,47 +23,24 @@
 namespace llc {
 
 constexpr uint32_t kFpTabLog = 12;                           // 4096 x u32, the size of the reference's table
-constexpr uint32_t kFpLaneMax = 36;                          // match bytes a lane extends on its own
-
-// One sequence, written by the whole warp: token | literal-length bytes | literals | offset | match-length bytes
-__device__ __forceinline__ void fp_emit(const uint8_t* __restrict__ src, uint8_t* dst, uint32_t& op, uint32_t anchor,
-                                        uint32_t ps, uint32_t offv, uint32_t ml, int lane) {
-    const uint32_t ll = ps - anchor, code = ml - 4u;
-    if ((ll < 15u) & (code < 15u)) {                         // at most 17 bytes: one byte per lane
-        uint32_t v = 0;
-        if ((uint32_t)(lane - 1) < ll) v = src[anchor + lane - 1];
-        if (lane == 0) v = (ll << 4) | code;
-        if ((uint32_t)lane == ll + 1u) v = offv;
-        if ((uint32_t)lane == ll + 2u) v = offv >> 8;
-        if ((uint32_t)lane <= ll + 2u) dst[op + lane] = (uint8_t)v;
-        op += ll + 3u;
-        return;
-    }
-    const uint32_t ll_ext = ll >= 15 ? (ll - 15) / 255 + 1 : 0;
-    const uint32_t ml_ext = code >= 15 ? (code - 15) / 255 + 1 : 0;
-    if (lane == 0) dst[op] = (uint8_t)((min(ll, 15u) << 4) | min(code, 15u));
-    if (ll_ext) lz4_put_ext(dst + op + 1, ll - 15, lane);
-    if (ll <= 32) { if ((uint32_t)lane < ll) dst[op + 1 + ll_ext + lane] = src[anchor + lane]; }
-    else warp_copy(dst + op + 1 + ll_ext, src + anchor, ll, lane);
-    op += 1 + ll_ext + ll;
-    if (lane == 0) { dst[op] = (uint8_t)offv; dst[op + 1] = (uint8_t)(offv >> 8); }
-    op += 2;
-    if (ml_ext) lz4_put_ext(dst + op, code - 15, lane);
-    op += ml_ext;
-}
+constexpr uint32_t kFpLaneMax = 12;                          // match bytes a lane extends on its own; longer ones by the warp
+constexpr int kFpHalves = 2;                                 // a round = kFpHalves x 32 positions
 
 // Encodes src[0, n) as LZ4 sequences at dst.  Same contract as lz4_encode_unit (unlimited output): returns the
 // body length; a non-final unit leaves its trailing literals to the stitch (*tail_len), the final one writes them.
-// `tab`: 4096 words of shared or global memory owned by this warp.
+// `tab`: 4096 words of shared or global memory owned by this warp; an entry is (position + 1) << 13 | 13 check bits
+// of the four bytes at that position (0: empty) -- atomicMax keeps the highest position per bucket, and a candidate
+// whose check bits differ is dropped without fetching it.
 //
-// A round covers kFpHalves x 32 consecutive positions, lane l taking positions t + l, t + 32 + l, ...: the loads of
-// the halves are independent, so their latencies (table word from L2, candidate bytes from L2 / HBM, the words of
-// the match extension) overlap -- the encoder is latency bound, one round is one dependent chain of ~6 memory
-// round trips.  All halves read the table as it was BEFORE the round and insert afterwards (atomicMax: the result
-// does not depend on the order of the lanes); a repeat closer than the round is found inside a half with
-// MATCH.ANY on the four bytes (the nearest earlier lane with the same bytes), which is what catches runs and the
-// short periods of columnar data.
-constexpr int kFpHalves = 2;
+// A round covers kFpHalves x 32 consecutive positions, lane l taking positions t + l, t + 32 + l: the loads of the
+// halves are independent, so their latencies (table word from L2, candidate bytes from L2 / HBM, the words of the
+// match extension) overlap.  All halves read the table as it was BEFORE the round and insert afterwards; a repeat
+// closer than that is found inside a half with MATCH.ANY on the four bytes (the nearest earlier lane with the same
+// bytes), which is what catches runs and the short periods of columnar data.
+// Per half: the greedy selection walks the matches in position order (uniform loop, a few instructions per
+// sequence: every lane learns whether it is a match start, a literal of which sequence, or covered); then the
+// sequences of the half are written LANE PARALLEL -- a warp scan of their sizes gives every sequence its place, the
+// start lanes write token / length bytes / offset, every literal lane writes its own byte.
 __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, bool emit_tail,
                                               uint32_t* tail_len, uint32_t* tab, int lane, InGate& gate) {
     const LeanSrc S(src);
@@ -84,20 +61,22 @@ __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, u
                 const uint32_t p = t + 32u * k + (uint32_t)lane;
                 inb[k] = p <= last_start;
                 v[k] = 0; h[k] = 0; e[k] = 0;
-                if (inb[k]) { v[k] = S.u32(p); h[k] = (v[k] * 2654435761U) >> (32u - kFpTabLog); e[k] = tab[h[k]]; }
+                if (p + 4u <= n) v[k] = S.u32(p);            // (also beyond last_start: the byte is needed as a literal)
+                if (inb[k]) { h[k] = (v[k] * 2654435761U) >> (32u - kFpTabLog); e[k] = tab[h[k]]; }
             }
             __syncwarp();                                    // every lane has read the old state
 #pragma unroll
             for (int k = 0; k < kFpHalves; k++) {
                 const uint32_t p = t + 32u * k + (uint32_t)lane;
-                if (inb[k]) atomicMax(&tab[h[k]], p + 1u);   // entry = position + 1 (0: empty)
+                const uint32_t chk = (v[k] * 0x9E3779B1u) >> 19;           // 13 bits, independent of the bucket bits
+                if (inb[k]) atomicMax(&tab[h[k]], ((p + 1u) << 13) | chk);
                 // the nearest earlier lane of this half with the same four bytes, else the table's candidate
                 const unsigned same = __match_any_sync(kFull, inb[k] ? v[k] : (0x80000000u | (uint32_t)lane) ^ v[k]) & lower;
                 ok[k] = false;
-                c[k] = e[k] - 1u;                            // < t: entries come from earlier rounds
+                c[k] = (e[k] >> 13) - 1u;                    // < t: entries come from earlier rounds
                 if (inb[k] && same) {                        // same four bytes by construction: nothing to verify
                     c[k] = t + 32u * k + (31u - (uint32_t)__clz(same)); ok[k] = true;
-                } else if (inb[k] && e[k] != 0u && (p - c[k]) <= 65535u) {
+                } else if (inb[k] && e[k] != 0u && (e[k] & 0x1fffu) == chk && (p - c[k]) <= 65535u) {
                     ok[k] = S.u32(c[k]) == v[k];
                 }
                 ml[k] = ok[k] ? 4u : 0u;
@@ -106,31 +85,27 @@ __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, u
             bool more[kFpHalves];
 #pragma unroll
             for (int k = 0; k < kFpHalves; k++) more[k] = ok[k];
-            for (;;) {
-                bool any = false;
+#pragma unroll
+            for (uint32_t it = 0; it < (kFpLaneMax - 4u) / 4u; it++) {
 #pragma unroll
                 for (int k = 0; k < kFpHalves; k++) {
                     const uint32_t p = t + 32u * k + (uint32_t)lane;
-                    more[k] = more[k] && ml[k] < kFpLaneMax && p + ml[k] + 4u <= mlimit;
+                    more[k] = more[k] && p + ml[k] + 4u <= mlimit;
                     if (more[k]) {
                         const uint32_t x = S.u32(p + ml[k]) ^ S.u32(c[k] + ml[k]);
                         if (x) { ml[k] += (uint32_t)(__ffs(x) - 1) >> 3; more[k] = false; }
                         else ml[k] += 4u;
                     }
-                    any = any || more[k];
                 }
-                if (!any) break;
             }
-#pragma unroll
-            for (int k = 0; k < kFpHalves; k++) {
-                const uint32_t p = t + 32u * k + (uint32_t)lane;
-                if (ok[k] && ml[k] < kFpLaneMax && p + ml[k] + 4u > mlimit)   // the last bytes before the limit, one at a time
-                    while (p + ml[k] < mlimit && src[p + ml[k]] == src[c[k] + ml[k]]) ml[k]++;
-            }
-            // greedy selection in position order
 #pragma unroll
             for (int k = 0; k < kFpHalves; k++) {
                 const uint32_t tk = t + 32u * k;
+                const uint32_t p = tk + (uint32_t)lane;
+                // ---- greedy selection in position order.  Afterwards: start = I begin a selected sequence (mlen, lit0
+                //      = where its literals begin), seq = the lane whose sequence I am a literal of (32: none)
+                bool start = false;
+                uint32_t mlen = 0, lit0 = 0, seq = 32u;
                 unsigned okm = __ballot_sync(kFull, ok[k]);
                 while (okm) {
                     const uint32_t arel = anchor > tk ? anchor - tk : 0u;     // first lane of this half that may start a match
@@ -142,8 +117,8 @@ __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, u
                     const uint32_t ps = tk + (uint32_t)s;
                     const uint32_t cs = __shfl_sync(kFull, c[k], s);
                     uint32_t mls = __shfl_sync(kFull, ml[k], s);
-                    if (mls >= kFpLaneMax) {
-                        // a long match: the warp extends it, lane j compares the word at +4j, 128 bytes per step
+                    if (mls >= kFpLaneMax && ps + mls + 4u <= mlimit) {
+                        // still equal after kFpLaneMax bytes: the warp extends it, lane j compares the word at +4j, 128 bytes per step
                         for (;;) {
                             const uint32_t q = mls + 4u * (uint32_t)lane;
                             uint32_t eq = 0;                              // equal bytes my word contributes
@@ -161,9 +136,42 @@ __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, u
                             }
                             mls += 128u;
                         }
+                    } else if (mls < kFpLaneMax && ps + mls + 4u > mlimit) {
+                        while (ps + mls < mlimit && src[ps + mls] == src[cs + mls]) mls++;    // the last bytes before the limit
                     }
-                    fp_emit(src, dst, op, anchor, ps, ps - cs, mls, lane);
+                    if (lane == s) { start = true; mlen = mls; lit0 = anchor; }
+                    if (p >= anchor && p < ps) seq = (uint32_t)s;
                     anchor = ps + mls;
+                }
+                // ---- lane-parallel emission of the half's sequences
+                const unsigned sel = __ballot_sync(kFull, start);
+                if (sel) {
+                    const uint32_t ll = p - lit0, code = mlen - 4u;
+                    const uint32_t ll_ext = (start && ll >= 15u) ? (ll - 15u) / 255u + 1u : 0u;
+                    const uint32_t ml_ext = (start && code >= 15u) ? (code - 15u) / 255u + 1u : 0u;
+                    const uint32_t size = start ? 1u + ll_ext + ll + 2u + ml_ext : 0u;
+                    const uint32_t incl = warp_incl_sum(size, lane);
+                    const uint32_t at = op + incl - size;                     // my sequence starts here
+                    const uint32_t litbase = at + 1u + ll_ext - lit0;         // literal at position q goes to dst[litbase + q]
+                    if (start) {
+                        dst[at] = (uint8_t)((min(ll, 15u) << 4) | min(code, 15u));
+                        if (ll_ext) { for (uint32_t j = 0; j + 1u < ll_ext; j++) dst[at + 1u + j] = 255; dst[at + ll_ext] = (uint8_t)((ll - 15u) % 255u); }
+                        const uint32_t o = at + 1u + ll_ext + ll, offv = p - c[k];
+                        dst[o] = (uint8_t)offv; dst[o + 1u] = (uint8_t)(offv >> 8);
+                        if (ml_ext) { for (uint32_t j = 0; j + 1u < ml_ext; j++) dst[o + 2u + j] = 255; dst[o + 1u + ml_ext] = (uint8_t)((code - 15u) % 255u); }
+                    }
+                    // literals inside the half: every such lane writes its own byte (the low byte of its four)
+                    const uint32_t lb = __shfl_sync(kFull, litbase, (int)(seq & 31u));
+                    if (seq < 32u) dst[lb + p] = (uint8_t)v[k];
+                    // literals in front of the half (left over by earlier rounds) belong to the first sequence
+                    const int s0 = __ffs(sel) - 1;
+                    const uint32_t l0 = __shfl_sync(kFull, lit0, s0), b0 = __shfl_sync(kFull, litbase, s0);
+                    if (l0 < tk) {
+                        const uint32_t pend = tk - l0;
+                        if (pend <= 32u) { if ((uint32_t)lane < pend) dst[b0 + l0 + lane] = src[l0 + lane]; }
+                        else warp_copy(dst + b0 + l0, src + l0, pend, lane);
+                    }
+                    op += __shfl_sync(kFull, incl, 31);
                 }
             }
             t = max(t + 32u * kFpHalves, anchor);            // the inside of a match that leaves the round is skipped
