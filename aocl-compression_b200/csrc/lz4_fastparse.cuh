@@ -169,7 +169,7 @@ __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, u
                     if (l0 < tk) {
                         const uint32_t pend = tk - l0;
                         if (pend <= 32u) { if ((uint32_t)lane < pend) dst[b0 + l0 + lane] = src[l0 + lane]; }
-                        else warp_copy(dst + b0 + l0, src + l0, pend, lane);
+                        else warp_copy(dst + (uint32_t)(b0 + l0), src + l0, pend, lane);   // (b0 is a difference: wrap in 32 bits first)
                     }
                     op += __shfl_sync(kFull, incl, 31);
                 }
