@@ -53,7 +53,7 @@ constexpr uint32_t kQCapMax = 0xfffe0000u;                   // output positions
 constexpr uint32_t kQInMax = 0xffffff00u;                    // stream positions stay below the marker codes
 constexpr uint32_t kPChunkLog = 8, kPChunk = 1u << kPChunkLog;   // parser window: four 256-byte chunks per unit
 constexpr uint32_t kPChunks = 4, kPWin = kPChunks * kPChunk, kPWinMask = kPWin - 1;
-constexpr uint32_t kQReach = 80;                             // a fast step touches stream bytes [ip, ip + kQReach)
+constexpr uint32_t kQReach = 84;                             // a fast step touches stream bytes [ip, ip + kQReach)
 constexpr uint32_t kQSpinMax = 1u << 20;                     // copier watchdog (~1 s of sleeping polls)
 constexpr uint32_t kUnitBad = 0x100u;                        // QUnit.flags: the unit header itself is malformed
 
@@ -126,6 +126,7 @@ struct QLane {
     uint32_t wbase;                    // shared-space address of the window
     uint32_t bar0;                     // shared-space address of its first mbarrier
     uint32_t w_issued, w_landed, wlim, wpar;   // wpar: bit b = parity of the next phase of buffer b
+    uint32_t pf_ip, pf0, pf1;          // the first two stream bytes at pf_ip, loaded one step ahead
     bool last, bad;
 };
 
@@ -176,30 +177,37 @@ __device__ __forceinline__ uint32_t qwin_u8(const QLane& s, uint32_t p) { return
 // Returns false (nothing consumed) for a 255 length byte or a literal run beyond the reach: general step.
 __device__ __forceinline__ bool qfast_lz4(QLane& s, uint32_t* q, uint32_t& tail) {
     const uint32_t ip = s.ip;
-    const uint32_t tok = qwin_u8(s, ip), e1 = qwin_u8(s, ip + 1u);
+    uint32_t tok = s.pf0, e1 = s.pf1;
+    if (s.pf_ip != ip) { tok = qwin_u8(s, ip); e1 = qwin_u8(s, ip + 1u); }
     const uint32_t nibL = tok >> 4, nibM = tok & 15u;
     const bool extL = nibL == 15u, extM = nibM == 15u;
     const uint32_t ll = extL ? 15u + e1 : nibL;
     const uint32_t rel = ll + (extL ? 2u : 1u);             // the offset field, relative to ip
+    const uint32_t ipn = ip + rel + 2u + (extM ? 1u : 0u);
+    // The chain token -> next token is all that is serial.  The next step's bytes are requested FIRST, the rest of
+    // this step (length byte of the match, checks, queue entry) runs while they are on their way.
+    s.pf0 = qwin_u8(s, ipn); s.pf1 = qwin_u8(s, ipn + 1u); s.pf_ip = ipn;
     const uint32_t e2 = qwin_u8(s, ip + rel + 2u);          // (garbage when rel is out of reach: rejected below)
     const uint32_t ml = nibM + 4u + (extM ? e2 : 0u);
-    if ((extL & (e1 == 255u)) | (extM & (e2 == 255u)) | (rel + 3u > kQReach)) return false;
+    if ((extL & (e1 == 255u)) | (extM & (e2 == 255u)) | (rel + 5u > kQReach)) { s.pf_ip = 0xffffffffu; return false; }   // (the look-ahead may have read past the window)
     q[tail & kQMask] = ip;
     tail++;
     s.op += ll + ml;
-    s.ip = ip + rel + 2u + (extM ? 1u : 0u);
+    s.ip = ipn;
     return true;
 }
 // FAST STEP, Snappy.  Precondition: ip < fast_i_ex (319 stream bytes ahead), ip + kQReach <= wlim.  Returns false
 // for a 4-byte-offset copy, a literal with length bytes, or an element that does not fit the output: general step.
 __device__ __forceinline__ bool qfast_snappy(QLane& s, uint32_t* q, uint32_t& tail) {
     const uint32_t ip = s.ip;
-    const uint32_t tag = qwin_u8(s, ip);
+    uint32_t tag = s.pf0;
+    if (s.pf_ip != ip) tag = qwin_u8(s, ip);
     const uint32_t kind = tag & 3u, hi = tag >> 2;
     const bool is_lit = kind == 0u;
     const uint32_t len = (kind == 1u) ? 4u + (hi & 7u) : hi + 1u;
     const uint32_t adv = is_lit ? 1u + len : (kind == 1u ? 2u : 3u);
-    if ((kind == 3u) | (is_lit & (hi >= 60u)) | (len > s.cap - s.op)) return false;
+    s.pf0 = qwin_u8(s, ip + adv); s.pf_ip = ip + adv;       // (an element the fast step refuses is at most 64 bytes ahead)
+    if ((kind == 3u) | (is_lit & (hi >= 60u)) | (len > s.cap - s.op)) { s.pf_ip = 0xffffffffu; return false; }
     q[tail & kQMask] = ip;
     tail++;
     s.op += len;
@@ -317,6 +325,7 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
     s.gbase = nullptr; s.ip = s.iend = s.op = s.cap = s.fast_i_ex = s.fast_o_ex = s.pad = 0;
     s.wbase = smem_u32(sh.pwin[slot]); s.bar0 = smem_u32(&sh.pbar[slot][0]);
     s.w_issued = s.w_landed = s.wlim = s.wpar = 0;
+    s.pf_ip = 0xffffffffu; s.pf0 = s.pf1 = 0;
     s.last = false; s.bad = false;
     u.in = nullptr; u.out = nullptr; u.clen = u.cap = u.flags = 0;
     uint32_t tail = 0, published = 0, head_c = 0;
@@ -325,12 +334,17 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
         if (sh.abort) break;
         // ---- fast steps: up to 8 sequences per lane back to back (the bookkeeping below runs once per pass)
         bool slow = !active;                                 // this lane needs the general code
+        // what bounds the pass, taken once: free queue entries, and how far the stream may be read
+        uint32_t left = active ? min(8u, kQCap - (tail - head_c)) : 0u;
+        const uint32_t ip_stop = min(s.fast_i_ex, s.wlim > kQReach ? s.wlim - kQReach : 0u);
 #pragma unroll 1
         for (int it = 0; it < 8; it++) {
-            const bool can = active && !slow && (tail - head_c < kQCap) && s.ip < s.fast_i_ex && (SNAPPY || s.op < s.fast_o_ex) &&
-                             s.ip + kQReach <= s.wlim;
+            const bool can = left != 0u && s.ip < ip_stop && (SNAPPY || s.op < s.fast_o_ex);
             if (!__any_sync(kFull, can)) break;
-            if (can && !(SNAPPY ? qfast_snappy(s, q, tail) : qfast_lz4(s, q, tail))) slow = true;
+            if (can) {
+                left--;
+                if (!(SNAPPY ? qfast_snappy(s, q, tail) : qfast_lz4(s, q, tail))) { slow = true; left = 0u; }
+            }
         }
         bool moved = false;
         if (alive) {
@@ -353,7 +367,7 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
                         s.pad = (uint32_t)(reinterpret_cast<uintptr_t>(u.in) & 15);
                         s.gbase = u.in - s.pad;
                         s.iend = u.clen + s.pad; s.cap = min(u.cap, kQCapMax);
-                        s.ip = s.pad; s.op = 0; s.bad = false;
+                        s.ip = s.pad; s.op = 0; s.bad = false; s.pf_ip = 0xffffffffu;
                         s.last = (u.flags & kPartLast) != 0;
                         const bool any_fast = u.clen >= 320u && (SNAPPY || s.cap >= 560u);
                         s.fast_i_ex = any_fast ? s.iend - 319u : 0u;

@@ -2,7 +2,7 @@
 """Summarise `ncu --set full` reports (gpurun_out/<tag>_{enc,dec,senc,sdec}.ncu-rep) into one JSON file:
 duration, DRAM bytes, issue utilisation, stall reasons per issue, instruction count of the captured launch.
 
-  python tools/ncu_summary.py <tag> profiles/<tag>_ncu_full_summary.json
+  python tools/ncu_summary.py <tag> profiles/<tag>_ncu_full_summary.json [key=path.ncu-rep ...]
 """
 import csv
 import io
@@ -39,6 +39,9 @@ def main():
         p = os.path.join("gpurun_out", f"{tag}_{key}.ncu-rep")
         if os.path.exists(p):
             out[key] = summarise(p)
+    for extra in sys.argv[3:]:
+        key, p = extra.split("=", 1)
+        out[key] = summarise(p)
     json.dump(out, open(dst, "w"), indent=1)
     for k, v in out.items():
         rd, wr = v.get("dram__bytes_read.sum", {}), v.get("dram__bytes_write.sum", {})
