@@ -54,6 +54,7 @@ constexpr uint32_t kQInMax = 0xffffff00u;                    // stream positions
 constexpr uint32_t kPChunkLog = 8, kPChunk = 1u << kPChunkLog;   // parser window: four 256-byte chunks per unit
 constexpr uint32_t kPChunks = 4, kPWin = kPChunks * kPChunk, kPWinMask = kPWin - 1;
 constexpr uint32_t kQReach = 84;                             // a fast step touches stream bytes [ip, ip + kQReach)
+constexpr uint32_t kQPass = 16;                              // fast steps per parser pass (queue bookkeeping runs once per pass)
 constexpr uint32_t kQSpinMax = 1u << 20;                     // copier watchdog (~1 s of sleeping polls)
 constexpr uint32_t kUnitBad = 0x100u;                        // QUnit.flags: the unit header itself is malformed
 
@@ -126,7 +127,7 @@ struct QLane {
     uint32_t wbase;                    // shared-space address of the window
     uint32_t bar0;                     // shared-space address of its first mbarrier
     uint32_t w_issued, w_landed, wlim, wpar;   // wpar: bit b = parity of the next phase of buffer b
-    uint32_t pf_ip, pf0, pf1;          // the first two stream bytes at pf_ip, loaded one step ahead
+    uint32_t pf0;                      // the stream byte at ip, requested one step ahead (valid inside a pass of fast steps)
     bool last, bad;
 };
 
@@ -177,19 +178,20 @@ __device__ __forceinline__ uint32_t qwin_u8(const QLane& s, uint32_t p) { return
 // Returns false (nothing consumed) for a 255 length byte or a literal run beyond the reach: general step.
 __device__ __forceinline__ bool qfast_lz4(QLane& s, uint32_t* q, uint32_t& tail) {
     const uint32_t ip = s.ip;
-    uint32_t tok = s.pf0, e1 = s.pf1;
-    if (s.pf_ip != ip) { tok = qwin_u8(s, ip); e1 = qwin_u8(s, ip + 1u); }
+    const uint32_t tok = s.pf0;                              // the token at ip, requested by the previous step
     const uint32_t nibL = tok >> 4, nibM = tok & 15u;
     const bool extL = nibL == 15u, extM = nibM == 15u;
-    const uint32_t ll = extL ? 15u + e1 : nibL;
+    uint32_t e1 = 0;
+    if (extL) e1 = qwin_u8(s, ip + 1u);                     // (a literal run of 15 or more: one more load on the chain)
+    const uint32_t ll = nibL + e1;
     const uint32_t rel = ll + (extL ? 2u : 1u);             // the offset field, relative to ip
     const uint32_t ipn = ip + rel + 2u + (extM ? 1u : 0u);
-    // The chain token -> next token is all that is serial.  The next step's bytes are requested FIRST, the rest of
-    // this step (length byte of the match, checks, queue entry) runs while they are on their way.
-    s.pf0 = qwin_u8(s, ipn); s.pf1 = qwin_u8(s, ipn + 1u); s.pf_ip = ipn;
+    // The chain token -> next token is all that is serial.  The next token is requested FIRST, the rest of this
+    // step (length byte of the match, checks, queue entry) runs while it is on its way.
+    s.pf0 = qwin_u8(s, ipn);
     const uint32_t e2 = qwin_u8(s, ip + rel + 2u);          // (garbage when rel is out of reach: rejected below)
     const uint32_t ml = nibM + 4u + (extM ? e2 : 0u);
-    if ((extL & (e1 == 255u)) | (extM & (e2 == 255u)) | (rel + 5u > kQReach)) { s.pf_ip = 0xffffffffu; return false; }   // (the look-ahead may have read past the window)
+    if ((extL & (e1 == 255u)) | (extM & (e2 == 255u)) | (rel + 5u > kQReach)) return false;   // (pf0 is stale now: the caller reloads)
     q[tail & kQMask] = ip;
     tail++;
     s.op += ll + ml;
@@ -200,14 +202,13 @@ __device__ __forceinline__ bool qfast_lz4(QLane& s, uint32_t* q, uint32_t& tail)
 // for a 4-byte-offset copy, a literal with length bytes, or an element that does not fit the output: general step.
 __device__ __forceinline__ bool qfast_snappy(QLane& s, uint32_t* q, uint32_t& tail) {
     const uint32_t ip = s.ip;
-    uint32_t tag = s.pf0;
-    if (s.pf_ip != ip) tag = qwin_u8(s, ip);
+    const uint32_t tag = s.pf0;
     const uint32_t kind = tag & 3u, hi = tag >> 2;
     const bool is_lit = kind == 0u;
     const uint32_t len = (kind == 1u) ? 4u + (hi & 7u) : hi + 1u;
     const uint32_t adv = is_lit ? 1u + len : (kind == 1u ? 2u : 3u);
-    s.pf0 = qwin_u8(s, ip + adv); s.pf_ip = ip + adv;       // (an element the fast step refuses is at most 64 bytes ahead)
-    if ((kind == 3u) | (is_lit & (hi >= 60u)) | (len > s.cap - s.op)) { s.pf_ip = 0xffffffffu; return false; }
+    s.pf0 = qwin_u8(s, ip + adv);                           // (an element the fast step refuses is at most 64 bytes ahead)
+    if ((kind == 3u) | (is_lit & (hi >= 60u)) | (len > s.cap - s.op)) return false;
     q[tail & kQMask] = ip;
     tail++;
     s.op += len;
@@ -216,7 +217,8 @@ __device__ __forceinline__ bool qfast_snappy(QLane& s, uint32_t* q, uint32_t& ta
 }
 
 // Marker with a fully parsed sequence (the general steps below; positions relative to the unit's first byte)
-__device__ __forceinline__ void qpush_seq(const QLane& s, uint32_t* q, uint32_t& tail, uint32_t lp, uint32_t ll, uint32_t off, uint32_t ml) {
+template <class S>
+__device__ __forceinline__ void qpush_seq(const S& s, uint32_t* q, uint32_t& tail, uint32_t lp, uint32_t ll, uint32_t off, uint32_t ml) {
     q[tail & kQMask] = kMarkSeq; q[(tail + 1u) & kQMask] = lp + s.pad; q[(tail + 2u) & kQMask] = ll;
     q[(tail + 3u) & kQMask] = off; q[(tail + 4u) & kQMask] = ml;
     tail += 5u;
@@ -225,7 +227,14 @@ __device__ __forceinline__ void qpush_seq(const QLane& s, uint32_t* q, uint32_t&
 // One LZ4 sequence through the general code (bytes straight from global memory): length runs, block tail, tiny
 // units -- every check of the reference.  Returns false when the unit is finished (ok or bad).  Positions in the
 // lane state are relative to gbase; the arithmetic below is relative to the unit's first byte.
-__device__ __noinline__ bool qlane_step_lz4(QLane& s, uint32_t* q, uint32_t& tail) {
+// State goes in and out BY VALUE: a noinline function that takes the lane state by reference forces the whole state
+// into local memory, and the fast loop then pays a dozen local loads / stores per pass.
+struct QSlow { uint32_t ip, op, tail; bool more, bad; };
+struct QSlowIn { const uint8_t* gbase; uint32_t pad, ip, iend, op, cap; bool last; };
+__device__ __noinline__ QSlow qlane_step_lz4(const QSlowIn a, uint32_t* q, uint32_t tail_in) {
+    struct { const uint8_t* gbase; uint32_t pad, ip, iend, op, cap; bool last, bad; } s = {a.gbase, a.pad, a.ip, a.iend, a.op, a.cap, a.last, false};
+    uint32_t tail = tail_in;
+    const bool more = [&]() -> bool {
     const uint8_t* in = s.gbase + s.pad;
     const uint32_t ip = s.ip - s.pad;
     const uint32_t iend = s.iend - s.pad, cap = s.cap;
@@ -265,10 +274,15 @@ __device__ __noinline__ bool qlane_step_lz4(QLane& s, uint32_t* q, uint32_t& tai
     s.ip = p + s.pad;
     if (!last && (s.op == cap || p >= iend)) return false;                           // lz4.c:4285-4288
     return true;
+    }();
+    return QSlow{s.ip, s.op, tail, more, s.bad};
 }
 
 // One Snappy element through the general code (cap is the exact size the stream must produce).
-__device__ __noinline__ bool qlane_step_snappy(QLane& s, uint32_t* q, uint32_t& tail) {
+__device__ __noinline__ QSlow qlane_step_snappy(const QSlowIn a, uint32_t* q, uint32_t tail_in) {
+    struct { const uint8_t* gbase; uint32_t pad, ip, iend, op, cap; bool last, bad; } s = {a.gbase, a.pad, a.ip, a.iend, a.op, a.cap, a.last, false};
+    uint32_t tail = tail_in;
+    const bool more = [&]() -> bool {
     const uint8_t* in = s.gbase + s.pad;
     const uint32_t ip = s.ip - s.pad, iend = s.iend - s.pad, expect = s.cap;
     if (ip >= iend) return false;
@@ -310,6 +324,8 @@ __device__ __noinline__ bool qlane_step_snappy(QLane& s, uint32_t* q, uint32_t& 
     s.op += len;
     s.ip = nip + s.pad;
     return true;
+    }();
+    return QSlow{s.ip, s.op, tail, more, s.bad};
 }
 
 // The parser warp: lane l owns slot l.  A lane that finishes a unit pushes the END marker (the copier reports the
@@ -325,7 +341,7 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
     s.gbase = nullptr; s.ip = s.iend = s.op = s.cap = s.fast_i_ex = s.fast_o_ex = s.pad = 0;
     s.wbase = smem_u32(sh.pwin[slot]); s.bar0 = smem_u32(&sh.pbar[slot][0]);
     s.w_issued = s.w_landed = s.wlim = s.wpar = 0;
-    s.pf_ip = 0xffffffffu; s.pf0 = s.pf1 = 0;
+    s.pf0 = 0;
     s.last = false; s.bad = false;
     u.in = nullptr; u.out = nullptr; u.clen = u.cap = u.flags = 0;
     uint32_t tail = 0, published = 0, head_c = 0;
@@ -334,17 +350,21 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
         if (sh.abort) break;
         // ---- fast steps: up to 8 sequences per lane back to back (the bookkeeping below runs once per pass)
         bool slow = !active;                                 // this lane needs the general code
-        // what bounds the pass, taken once: free queue entries, and how far the stream may be read
-        uint32_t left = active ? min(8u, kQCap - (tail - head_c)) : 0u;
+        // What bounds the pass, taken once: free queue entries, how far the stream may be read, and how many steps
+        // certainly stay inside the output region where no end rule can fire (a step produces < 544 bytes).
         const uint32_t ip_stop = min(s.fast_i_ex, s.wlim > kQReach ? s.wlim - kQReach : 0u);
+        uint32_t left = 0;
+        if (active) {
+            left = min(kQPass, kQCap - (tail - head_c));
+            if (!SNAPPY) left = min(left, s.fast_o_ex > s.op ? (s.fast_o_ex - s.op + 543u) / 544u : 0u);
+            if (s.ip >= ip_stop) left = 0;
+            if (left) s.pf0 = qwin_u8(s, s.ip);
+        }
 #pragma unroll 1
-        for (int it = 0; it < 8; it++) {
-            const bool can = left != 0u && s.ip < ip_stop && (SNAPPY || s.op < s.fast_o_ex);
+        for (uint32_t it = 0; it < kQPass; it++) {
+            const bool can = it < left && s.ip < ip_stop;
             if (!__any_sync(kFull, can)) break;
-            if (can) {
-                left--;
-                if (!(SNAPPY ? qfast_snappy(s, q, tail) : qfast_lz4(s, q, tail))) { slow = true; left = 0u; }
-            }
+            if (can && !(SNAPPY ? qfast_snappy(s, q, tail) : qfast_lz4(s, q, tail))) { slow = true; left = 0u; }
         }
         bool moved = false;
         if (alive) {
@@ -367,7 +387,7 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
                         s.pad = (uint32_t)(reinterpret_cast<uintptr_t>(u.in) & 15);
                         s.gbase = u.in - s.pad;
                         s.iend = u.clen + s.pad; s.cap = min(u.cap, kQCapMax);
-                        s.ip = s.pad; s.op = 0; s.bad = false; s.pf_ip = 0xffffffffu;
+                        s.ip = s.pad; s.op = 0; s.bad = false;
                         s.last = (u.flags & kPartLast) != 0;
                         const bool any_fast = u.clen >= 320u && (SNAPPY || s.cap >= 560u);
                         s.fast_i_ex = any_fast ? s.iend - 319u : 0u;
@@ -387,7 +407,12 @@ __device__ inline void rowq_parse(QShared& sh, const Src& src, uint32_t nunits, 
                         }
                     }
                 } else {
-                    const bool more = !s.bad && (SNAPPY ? qlane_step_snappy(s, q, tail) : qlane_step_lz4(s, q, tail));
+                    bool more = false;
+                    if (!s.bad) {
+                        const QSlowIn a{s.gbase, s.pad, s.ip, s.iend, s.op, s.cap, s.last};
+                        const QSlow r = SNAPPY ? qlane_step_snappy(a, q, tail) : qlane_step_lz4(a, q, tail);
+                        s.ip = r.ip; s.op = r.op; tail = r.tail; s.bad = r.bad; more = r.more;
+                    }
                     if (!more) {
                         const bool failed = s.bad || (SNAPPY && s.op != s.cap);            // snappy.cc:1715
                         q[tail & kQMask] = kMarkEnd; q[(tail + 1u) & kQMask] = failed ? 1u : 0u; q[(tail + 2u) & kQMask] = s.op; tail += 3u;
