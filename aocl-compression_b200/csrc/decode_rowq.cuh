@@ -38,7 +38,7 @@
 namespace llc {
 
 constexpr int kQSlots = 28;                                  // units in flight per CTA = copier warps
-constexpr int kQThreads = 32 * (kQSlots + 1);
+constexpr int kQThreads = 1024;                              // 32 warps: 1 parser, 28 copiers, 3 that leave at once (see rowq_run)
 constexpr uint32_t kQCap = 64, kQMask = kQCap - 1;           // 32-bit entries per unit queue
 constexpr uint32_t kQStride = kQCap + 1;                     // +1 entry: parser lanes hit different banks
 constexpr uint32_t kQRoom = 8;                               // free entries a lane wants before it pushes a marker
@@ -51,8 +51,8 @@ constexpr uint32_t kMarkEnd = kMarkBase + 2;                 // + failed (0 / 1)
 constexpr uint32_t kMarkQuit = kMarkBase + 3;
 constexpr uint32_t kQCapMax = 0xfffe0000u;                   // output positions + ring size must not wrap
 constexpr uint32_t kQInMax = 0xffffff00u;                    // stream positions stay below the marker codes
-constexpr uint32_t kPChunkLog = 8, kPChunk = 1u << kPChunkLog;   // parser window: four 256-byte chunks per unit
-constexpr uint32_t kPChunks = 4, kPWin = kPChunks * kPChunk, kPWinMask = kPWin - 1;
+constexpr uint32_t kPChunkLog = 9, kPChunk = 1u << kPChunkLog;   // parser window: two 512-byte chunks per unit
+constexpr uint32_t kPChunks = 2, kPWin = kPChunks * kPChunk, kPWinMask = kPWin - 1;
 constexpr uint32_t kQReach = 84;                             // a fast step touches stream bytes [ip, ip + kQReach)
 constexpr uint32_t kQPass = 16;                              // fast steps per parser pass (queue bookkeeping runs once per pass)
 constexpr uint32_t kQSpinMax = 1u << 20;                     // copier watchdog (~1 s of sleeping polls)
@@ -150,12 +150,14 @@ __device__ __forceinline__ void qwin_wait(QLane& s, uint32_t c) {
     } while (!ok);
     s.wpar ^= 1u << b;
 }
-// Keep chunks up to (chunk of ip) + 2 requested and up to (chunk of ip) + 1 landed.  A chunk goes into buffer
-// (chunk & 3), i.e. over chunk - 4, which lies behind ip.
+// Keep the chunk of ip and the following kPChunks - 1 requested, and up to (chunk of ip) + 1 landed.  A chunk goes into
+// buffer (chunk mod kPChunks), i.e. over chunk - kPChunks, which lies behind ip.
 __device__ __forceinline__ void qwin_fill(QLane& s) {
     const uint32_t c = s.ip >> kPChunkLog;
-    while (s.w_issued < c + 3u && (s.w_issued << kPChunkLog) < s.iend) { qwin_issue(s, s.w_issued); s.w_issued++; }
-    const uint32_t want = min(c + 2u, s.w_issued);
+    while (s.w_issued < c + kPChunks && (s.w_issued << kPChunkLog) < s.iend) { qwin_issue(s, s.w_issued); s.w_issued++; }
+    // wait only for what the next steps can touch: the following chunk was requested a whole chunk ago and is
+    // waited for when ip comes close to it (waiting for a chunk right after requesting it stalls all 28 lanes)
+    const uint32_t want = min(((s.ip + 2u * kQReach) >> kPChunkLog) + 1u, s.w_issued);
     while (s.w_landed < want) { qwin_wait(s, s.w_landed); s.w_landed++; }
     s.wlim = s.w_landed << kPChunkLog;
 }
@@ -652,8 +654,12 @@ __device__ __forceinline__ void rowq_run(QShared& sh, const Src& src, uint32_t n
         fence_mbar_init();
     }
     __syncthreads();
+    // Warp w issues from scheduler w mod 4.  The parser warp is a single dependent chain that sets the pace of the
+    // whole CTA, so it gets scheduler 0 almost to itself: warps 4, 8 and 12 leave at once, scheduler 0 keeps the
+    // parser and 4 copiers, the other three schedulers take 8 copiers each.
     if (warp == 0) rowq_parse<SNAPPY>(sh, src, nunits, ticket, lane);
-    else rowq_copy<SNAPPY>(sh, src, warp - 1, lane);
+    else if (warp & 3) rowq_copy<SNAPPY>(sh, src, (warp >> 2) * 3 + (warp & 3) - 1, lane);
+    else if (warp >= 16) rowq_copy<SNAPPY>(sh, src, 24 + ((warp - 16) >> 2), lane);
 }
 
 }  // namespace llc
