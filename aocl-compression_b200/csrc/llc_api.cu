@@ -17,11 +17,14 @@
 #include "../../include/aocl_llc_native.h"
 
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include <time.h>
 
@@ -314,6 +317,147 @@ int64_t decompress_pipelined(HostCtx& h, int codec, const char* in, size_t n, ch
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// ONE call over several GPUs (AOCL_GPU_SHARD=1 with two or more devices in AOCL_GPU_DEVICES; host buffers).
+// The reference forks OpenMP threads over the partitions of a frame (lz4.c:2684-2731, threads/threads.c:121-153);
+// here one host thread per GPU takes a contiguous partition range: it uploads only its slice over its own PCIe
+// link, runs the sharded device call (csrc/llc_shard.cuh: the GPUs exchange the per-partition records and the
+// boundary literals over NCCL) and downloads its piece straight to its final place in the caller's buffer.
+// ------------------------------------------------------------------------------------------------
+struct ShardGroup {
+    std::mutex mu;                     // one sharded call at a time
+    std::vector<HostCtx*> rank;        // one dedicated context per device, NCCL communicator joined
+    bool ready = false, failed = false;
+};
+ShardGroup sg;
+constexpr size_t kShardMinBytes = size_t(32) << 20;
+
+bool shard_wanted() {
+    const char* e = getenv("AOCL_GPU_SHARD");
+    return e && atoi(e) != 0;
+}
+
+// Creates the per-device contexts and the communicator (once).  Call with sg.mu held.
+bool shard_group_init() {
+    if (sg.ready) return true;
+    if (sg.failed) return false;
+    std::vector<int> devs;
+    {
+        std::lock_guard<std::mutex> lock(g.mu);
+        if (!g.init_done) { g.init_done = true; parse_devices_locked(); if (g.devices.empty()) g.init_failed = true; }
+        devs = g.devices;
+    }
+    const int R = (int)devs.size();
+    unsigned char id[128];
+    if (R < 2 || aocl_gpu_shard_unique_id(id) != 0) { sg.failed = true; return false; }
+    sg.rank.assign(R, nullptr);
+    std::vector<std::thread> th;
+    std::atomic<int> bad{0};
+    for (int r = 0; r < R; r++)
+        th.emplace_back([&, r] {
+            HostCtx* h = new HostCtx();
+            h->device = devs[r];
+            sg.rank[r] = h;
+            DeviceGuard guard(h->device);
+            if (aocl_gpu_ctx_create(&h->ctx, h->device, nullptr) != 0 || aocl_gpu_shard_init(h->ctx, id, r, R) != 0) bad++;
+        });
+    for (auto& t : th) t.join();
+    if (bad.load()) { sg.failed = true; return false; }
+    sg.ready = true;
+    return true;
+}
+
+// Returns bytes produced, -1 on failure, -100 when the call does not qualify (the caller takes the one-GPU path).
+int64_t run_codec_sharded(bool compress, int codec, char* in, size_t in_size, char* out, size_t out_size) {
+    if (in_size < kShardMinBytes || in_size > 0x7E000000ull) return -100;
+    if (compress && codec == LZ4) {                          // optOff / AOCL_DISABLE_OPT: one frame-less block, nothing to shard
+        std::lock_guard<std::mutex> lock(g.mu);
+        if (g.lz4_frameless) return -100;
+    }
+    std::lock_guard<std::mutex> lock(sg.mu);
+    if (!shard_group_init()) return -100;
+    const int R = (int)sg.rank.size();
+    uint32_t T = 0;
+    std::vector<uint64_t> in_lo(R), in_hi(R), out_need(R);
+    uint64_t head_bytes = 0;                                  // decompress: frame header (+ varint) every rank needs
+    if (compress) {
+        T = (uint32_t)aocl_gpu_partition_count(codec, in_size);
+        if (T < (uint32_t)R * 2u) return -100;
+        for (int r = 0; r < R; r++) {
+            uint32_t first, count; uint64_t off, len;
+            if (aocl_gpu_shard_range(codec, in_size, r, R, &first, &count, &off, &len) != 0) return -100;
+            in_lo[r] = off; in_hi[r] = off + len;
+            out_need[r] = aocl_gpu_compress_bound(codec, len) + 16 + 12 * (uint64_t)T + 64;
+        }
+    } else {
+        const unsigned char* u = (const unsigned char*)in;
+        uint64_t magic = 0;
+        if (in_size < 16) return -100;
+        memcpy(&magic, u, 8);
+        if (magic != kRapMagic) return -100;
+        const uint32_t frame = rd32(u + 8);
+        T = rd32(u + 12);
+        if (T < (uint32_t)R * 2u || T > 65536 || frame != 16 + 12 * (uint64_t)T || frame > in_size) return -100;
+        head_bytes = std::min<uint64_t>(in_size, (uint64_t)frame + 8);
+        uint64_t pos = frame, total = 0;
+        for (int r = 0; r < R; r++) {
+            const uint32_t lo = (uint32_t)((uint64_t)T * r / R), hi = (uint32_t)((uint64_t)T * (r + 1) / R);
+            uint64_t first_off = 0, need = 0;
+            bool seen = false;
+            for (uint32_t i = lo; i < hi; i++) {
+                const unsigned char* e = u + 16 + 12 * (size_t)i;
+                const uint64_t off = rd32(e), clen = rd32(e + 4), dlen = rd32(e + 8);
+                if (!clen) continue;
+                if (off < pos || off + clen > in_size) return -100;          // not laid out back to back: the plain path decides
+                if (!seen) { first_off = off; seen = true; }
+                pos = off + clen;
+                need += dlen;
+            }
+            in_lo[r] = seen ? first_off : pos; in_hi[r] = pos; out_need[r] = need;
+            total += need;
+        }
+        if (total > out_size) return -1;
+    }
+    std::vector<int64_t> result(R, -1);
+    std::vector<uint64_t> piece_off(R, 0), piece_len(R, 0);
+    std::atomic<int> alloc_bad{0}, arrived{0};
+    std::vector<std::thread> th;
+    for (int r = 0; r < R; r++)
+        th.emplace_back([&, r] {
+            HostCtx& h = *sg.rank[r];
+            DeviceGuard guard(h.device);
+            cudaStream_t s = (cudaStream_t)aocl_gpu_ctx_stream(h.ctx);
+            // all allocations first, then agree: nobody enters a collective unless everybody can
+            const size_t need_in = compress ? (size_t)(in_hi[r] - in_lo[r]) : in_size;
+            const bool ok_alloc = grow(h, &h.d_in, &h.d_in_bytes, need_in ? need_in : 1) && grow(h, &h.d_out, &h.d_out_bytes, out_need[r] ? out_need[r] : 1);
+            if (!ok_alloc) alloc_bad++;
+            arrived++;
+            while (arrived.load() < R) std::this_thread::yield();
+            if (alloc_bad.load()) return;
+            uint64_t off = 0, len = 0;
+            int64_t tot;
+            if (compress) {
+                cudaMemcpyAsync(h.d_in, in + in_lo[r], in_hi[r] - in_lo[r], cudaMemcpyHostToDevice, s);
+                tot = aocl_gpu_compress_sharded(h.ctx, codec, h.d_in, in_size, h.d_out, out_need[r], &off, &len);
+                if (tot > 0 && off + len <= out_size && cudaMemcpyAsync(out + off, h.d_out, len, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+                    cudaStreamSynchronize(s) == cudaSuccess) result[r] = tot;
+                else if (tot > 0) result[r] = -1;
+            } else {
+                cudaMemcpyAsync(h.d_in, in, head_bytes, cudaMemcpyHostToDevice, s);
+                if (in_hi[r] > in_lo[r]) cudaMemcpyAsync((char*)h.d_in + in_lo[r], in + in_lo[r], in_hi[r] - in_lo[r], cudaMemcpyHostToDevice, s);
+                tot = aocl_gpu_decompress_sharded(h.ctx, codec, h.d_in, in_size, h.d_out, out_need[r], &off, &len);
+                if (tot >= 0 && off + len <= out_size && (len == 0 || cudaMemcpyAsync(out + off, h.d_out, len, cudaMemcpyDeviceToHost, s) == cudaSuccess) &&
+                    cudaStreamSynchronize(s) == cudaSuccess) result[r] = tot;
+            }
+            piece_off[r] = off; piece_len[r] = len;
+            cudaGetLastError();
+        });
+    for (auto& t : th) t.join();
+    if (alloc_bad.load()) return -1;
+    for (int r = 0; r < R; r++) if (result[r] < 0 || result[r] != result[0]) return -1;
+    return result[0];
+}
+
 // Returns bytes produced or a negative codec error (the adapters' CODEC_ERROR).
 int64_t run_codec(bool compress, int codec, char* in, size_t in_size, char* out, size_t out_size) {
     if (compress) {
@@ -323,6 +467,10 @@ int64_t run_codec(bool compress, int codec, char* in, size_t in_size, char* out,
         if (in == nullptr || in_size == 0) return -1;                                        // lz4.c:3822, 3859
         if (out == nullptr && out_size != 0) return -1;
         if (codec == LZ4 && out == nullptr) return -1;
+    }
+    if (shard_wanted() && (in_size ? !on_device(in) : false) && !on_device(out)) {
+        const int64_t r = run_codec_sharded(compress, codec, in, in_size, out, out_size);
+        if (r != -100) return r;
     }
     Lease lease;                                            // one context for the whole call; other threads take others
     if (!lease.h) return -1;

@@ -49,3 +49,40 @@ def test_one_frame_on_two_gpus_matches_the_oracle():
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "shard_check.py")],
                        capture_output=True, text=True, cwd=ROOT, timeout=900)
     assert r.returncode == 0 and "SHARD CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+_HOST_SPLIT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.join(ROOT, "aocl-compression_b200", "python")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import llc_b200, oracle_lib as ol
+from llc_b200 import gen
+lib = ol.LlcLib(llc_b200.LIB_PATH)
+orc = ol.Oracle()
+rng = np.random.default_rng(4)
+cases = {"text": gen.text_like(72 << 20, seed=91),
+         "text+random": np.concatenate([gen.text_like(20 << 20, seed=92), rng.integers(0, 256, 14 << 20, dtype=np.uint8), gen.log_like(8 << 20, seed=93)])}
+for name, data in cases.items():
+    for codec in (0, 4):
+        want = orc.compress(data, codec)
+        r, got = lib.compress(data, codec)
+        assert r == len(want) and got == want, (name, codec, r, len(want))
+        r2, back = lib.decompress(got, codec, len(data))
+        assert r2 == len(data) and back == data.tobytes(), (name, codec, r2)
+        print("ok", name, codec, r)
+print("HOST SPLIT OK", llc_b200.load().aocl_gpu_launch_count())
+"""
+
+
+@pytest.mark.gpu
+def test_one_host_call_over_two_gpus():
+    """AOCL_GPU_DEVICES=0,1 AOCL_GPU_SHARD=1: aocl_llc_compress / aocl_llc_decompress split ONE host call over both GPUs
+    (a worker thread per device, slices over both PCIe links, NCCL between the GPUs) and still produce the oracle's
+    bytes -- including a frame whose incompressible middle hands literals from one GPU's partitions to the other's."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    env = dict(os.environ, AOCL_GPU_DEVICES="0,1", AOCL_GPU_SHARD="1")
+    env.pop("AOCL_GPU_DEVICE", None)
+    r = subprocess.run([sys.executable, "-c", f"ROOT = {ROOT!r}\n" + _HOST_SPLIT], env=env, capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0 and "HOST SPLIT OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
