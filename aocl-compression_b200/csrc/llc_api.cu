@@ -330,6 +330,7 @@ struct ShardGroup {
     bool ready = false, failed = false;
 };
 ShardGroup sg;
+std::atomic<uint64_t> g_sharded_calls{0};
 constexpr size_t kShardMinBytes = size_t(32) << 20;
 
 bool shard_wanted() {
@@ -455,6 +456,7 @@ int64_t run_codec_sharded(bool compress, int codec, char* in, size_t in_size, ch
     for (auto& t : th) t.join();
     if (alloc_bad.load()) return -1;
     for (int r = 0; r < R; r++) if (result[r] < 0 || result[r] != result[0]) return -1;
+    g_sharded_calls++;
     return result[0];
 }
 
@@ -581,6 +583,9 @@ extern "C" void aocl_llc_destroy(aocl_compression_desc* h, aocl_compression_type
     if (codec_type == LZ4) { g.lz4_setup_done = false; g.lz4_frameless = false; }   // lz4.c:5012-5016
     if (codec_type == SNAPPY) g.snappy_setup_done = false;
 }
+
+// Calls that were split over several GPUs so far (AOCL_GPU_SHARD=1); diagnostics / tests.
+extern "C" uint64_t aocl_gpu_sharded_host_calls(void) { return g_sharded_calls.load(); }
 
 extern "C" const char* aocl_llc_version(void) {
     return "AOCL-Compression 4.2.0 B200 LZ4/Snappy RAP path, Build " AOCL_LLC_BUILD_TAG;

@@ -68,7 +68,7 @@ GPU_API = ["aocl_gpu_ctx_create", "aocl_gpu_ctx_destroy", "aocl_gpu_ctx_stream",
            "aocl_gpu_debug_counters", "aocl_gpu_set_input_watermark", "aocl_gpu_decompress_open_async",
            "aocl_gpu_decompress_slab_async", "aocl_gpu_decompress_close_async",
            "aocl_gpu_shard_unique_id", "aocl_gpu_shard_init", "aocl_gpu_shard_destroy", "aocl_gpu_shard_range",
-           "aocl_gpu_compress_sharded", "aocl_gpu_decompress_sharded", "aocl_gpu_set_mode"]
+           "aocl_gpu_compress_sharded", "aocl_gpu_decompress_sharded", "aocl_gpu_set_mode", "aocl_gpu_sharded_host_calls"]
 
 _lib = None
 
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
         "aocl_gpu_decompress_slab_async": (i32, [vp, i32, vp, vp, u32, u32]),
         "aocl_gpu_decompress_close_async": (i32, [vp]),
         "aocl_gpu_set_mode": (i32, [vp, C.c_char_p]),
+        "aocl_gpu_sharded_host_calls": (u64, []),
         "aocl_gpu_shard_unique_id": (i32, [vp]),
         "aocl_gpu_shard_init": (i32, [vp, vp, i32, i32]),
         "aocl_gpu_shard_destroy": (None, [vp]),

@@ -144,6 +144,10 @@ int32_t aocl_gpu_compress_batch_async(aocl_gpu_ctx_t ctx, int32_t codec, const v
                                       const uint32_t *d_in_sizes, void *const *d_out_ptrs,
                                       const uint32_t *d_out_caps, int64_t *d_status, size_t count);
 
+/* aocl_llc_compress / aocl_llc_decompress calls that were split over several GPUs so far (AOCL_GPU_SHARD=1 with two
+ * or more devices in AOCL_GPU_DEVICES; host buffers of at least 32 MiB). */
+uint64_t aocl_gpu_sharded_host_calls(void);
+
 /* Number of kernels this library has launched in the calling process (bench.py reports it). */
 uint64_t aocl_gpu_launch_count(void);
 

@@ -52,7 +52,7 @@ def test_one_frame_on_two_gpus_matches_the_oracle():
 
 
 _HOST_SPLIT = r"""
-import os, sys
+import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.join(ROOT, "aocl-compression_b200", "python")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import llc_b200, oracle_lib as ol
@@ -70,7 +70,10 @@ for name, data in cases.items():
         r2, back = lib.decompress(got, codec, len(data))
         assert r2 == len(data) and back == data.tobytes(), (name, codec, r2)
         print("ok", name, codec, r)
-print("HOST SPLIT OK", llc_b200.load().aocl_gpu_launch_count())
+L = C.CDLL(llc_b200.LIB_PATH)
+L.aocl_gpu_sharded_host_calls.restype = C.c_uint64
+assert L.aocl_gpu_sharded_host_calls() == 8, L.aocl_gpu_sharded_host_calls()      # 2 inputs x 2 codecs x (compress + decompress)
+print("HOST SPLIT OK", L.aocl_gpu_sharded_host_calls())
 """
 
 
