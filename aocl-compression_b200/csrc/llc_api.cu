@@ -370,7 +370,7 @@ bool shard_group_init() {
 
 // Returns bytes produced, -1 on failure, -100 when the call does not qualify (the caller takes the one-GPU path).
 int64_t run_codec_sharded(bool compress, int codec, char* in, size_t in_size, char* out, size_t out_size) {
-    if (in_size < kShardMinBytes || in_size > 0x7E000000ull) return -100;
+    if ((compress ? in_size : out_size) < kShardMinBytes || in_size > 0x7E000000ull) return -100;
     if (compress && codec == LZ4) {                          // optOff / AOCL_DISABLE_OPT: one frame-less block, nothing to shard
         std::lock_guard<std::mutex> lock(g.mu);
         if (g.lz4_frameless) return -100;
