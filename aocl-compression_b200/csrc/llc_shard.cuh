@@ -186,12 +186,15 @@ extern "C" int64_t aocl_gpu_compress_sharded(aocl_gpu_ctx_t c, int32_t codec, co
         mine = S.h_info[0];
         bool fail = mine.total == 0;
         for (int r = 0; r < R; r++) fail = fail || S.h_info[1 + r].total == 0;
-        if (fail || mine.out_hi - mine.out_lo > out_cap) { c->last_rc = -2; return -2; }
-        // boundary literals: rank g needs the halo_g input bytes in front of its slice; they belong to ranks h < g
+        if (fail) { c->last_rc = -2; return -2; }            // the plan failed: it is the same plan on every rank, all of them leave here
+        // From here on a rank with a LOCAL problem (its piece does not fit, no memory for the inherited literals) must
+        // not simply leave: its neighbours are about to exchange boundary literals with it.  It still serves their
+        // requests from its input slice, skips its own receive side into a dummy, skips its compaction, and fails.
+        bool local_fail = mine.out_hi - mine.out_lo > out_cap;
         if (mine.halo > S.halo_bytes) {
             if (S.halo) cudaFree(S.halo);
             S.halo_bytes = (size_t)align_up((size_t)mine.halo, 1 << 16);
-            if (cudaMalloc(&S.halo, S.halo_bytes) != cudaSuccess) { cudaGetLastError(); S.halo = nullptr; S.halo_bytes = 0; c->last_rc = -2; return -2; }
+            if (cudaMalloc(&S.halo, S.halo_bytes) != cudaSuccess) { cudaGetLastError(); S.halo = nullptr; S.halo_bytes = 0; local_fail = true; }
         }
         bool any = false;
         for (int gk = 1; gk < R; gk++) any = any || S.h_info[1 + gk].halo != 0;
@@ -206,11 +209,17 @@ extern "C" int64_t aocl_gpu_compress_sharded(aocl_gpu_ctx_t c, int32_t codec, co
                     const uint64_t x0 = std::max(lo, Sh), x1 = std::min(Sg, Sh1);
                     if (x0 >= x1) continue;
                     if (me == h) ok = shard_ok(a.Send(src + (x0 - my_off), (size_t)(x1 - x0), ncclUint8, gk, S.comm, st), "Send(halo)");
-                    if (me == gk) ok = shard_ok(a.Recv(S.halo + (x0 - lo), (size_t)(x1 - x0), ncclUint8, h, S.comm, st), "Recv(halo)");
+                    if (me == gk) {
+                        // (no halo buffer: receive into the scratch area, which the skipped compaction will not read)
+                        uint8_t* into = S.halo ? S.halo + (x0 - lo) : scratch;
+                        if (!S.halo && (x1 - x0) > slot * (uint64_t)cnt) { ok = false; break; }
+                        ok = shard_ok(a.Recv(into, (size_t)(x1 - x0), ncclUint8, h, S.comm, st), "Recv(halo)");
+                    }
                 }
             }
             ok = shard_ok(a.GroupEnd(), "GroupEnd") && ok;
         }
+        if (local_fail) { cudaStreamSynchronize(st); c->last_rc = -2; return -2; }
         LLC_LAUNCH(lz4_compact_kernel, cnt, 256, 0, st, src, my_off, (const uint8_t*)S.halo, (uint64_t)mine.halo, scratch, slot, rec, plan, p0, dst,
                    (uint64_t)mine.out_lo, c->d_res);
     } else {

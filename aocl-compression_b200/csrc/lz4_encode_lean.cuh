@@ -343,6 +343,9 @@ __device__ inline uint32_t lz4_encode_warp_lean(const uint8_t* __restrict__ src,
 // encoder; small units (byU16 / hash4, n < 65547) and oversized frame-less blocks keep the fused one.
 __device__ inline uint32_t lz4_encode_unit(const uint8_t* src, uint32_t n, uint8_t* dst, int64_t cap, bool emit_tail,
                                            uint32_t* tail_len, uint32_t* tab_mem, uint8_t* own, int lane, InGate& gate) {
+    // (keeps the unit's input and output addresses in register pairs: under the register cap of the partition kernels
+    //  the compiler would rather rebuild them from the kernel parameters in front of an access)
+    asm volatile("" : "+l"(src), "+l"(dst));
 #ifndef LLC_LZ4_ENCODER_FUSED
     if (n >= 65547u && n < kLeanMaxUnit) return lz4_encode_warp_lean(src, n, dst, cap, emit_tail, tail_len, tab_mem, own, lane, gate);
 #endif

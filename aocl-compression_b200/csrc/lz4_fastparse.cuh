@@ -26,6 +26,12 @@ constexpr uint32_t kFpTabLog = 12;                           // 4096 x u32, the 
 constexpr uint32_t kFpLaneMax = 12;                          // match bytes a lane extends on its own; longer ones by the warp
 constexpr int kFpHalves = 2;                                 // a round = kFpHalves x 32 positions
 
+// Lane l < 20 loads aligned word (byte_off >> 2) + l of the input (0 where the word starts behind the unit's end).
+__device__ __forceinline__ uint32_t fp_window(const uint32_t* words, uint32_t byte_off, uint32_t end_off, int lane) {
+    const uint32_t wi = (byte_off >> 2) + (uint32_t)lane;
+    return (lane < 20 && wi * 4u < end_off) ? words[wi] : 0u;
+}
+
 // Encodes src[0, n) as LZ4 sequences at dst.  Same contract as lz4_encode_unit (unlimited output): returns the
 // body length; a non-final unit leaves its trailing literals to the stitch (*tail_len), the final one writes them.
 // `tab`: 4096 words of shared or global memory owned by this warp; an entry is (position + 1) << 13 | 13 check bits
@@ -43,7 +49,13 @@ constexpr int kFpHalves = 2;                                 // a round = kFpHal
 // start lanes write token / length bytes / offset, every literal lane writes its own byte.
 __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, bool emit_tail,
                                               uint32_t* tail_len, uint32_t* tab, int lane, InGate& gate) {
+    // (keeps the unit's input and output addresses in register pairs: under the register cap the compiler would
+    //  rather rebuild them from the kernel parameters in front of every access, five instructions each)
+    asm volatile("" : "+l"(src), "+l"(dst));
     const LeanSrc S(src);
+    // the input as aligned words: src[i] is byte i + mis of words[]
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t* const words = reinterpret_cast<const uint32_t*>(src - mis);
     uint32_t op = 0, anchor = 0;
     if (n >= 13u) {                                          // lz4.c:1926: shorter inputs are all literals
         for (uint32_t i = lane; i < (1u << kFpTabLog); i += 32) tab[i] = 0;
@@ -51,17 +63,31 @@ __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, u
         const uint32_t last_start = n - 12u;                 // a match starts at least 12 bytes before the end (MFLIMIT)
         const uint32_t mlimit = n - 5u;                      // ... and ends at least 5 bytes before it (LASTLITERALS)
         const uint32_t lower = (1u << lane) - 1u;            // lanes below mine
-        uint32_t t = 0;
+        uint32_t t = 0, W = 0, w_at = 0xffffffffu;            // W: the window of words at position w_at
         while (t <= last_start) {
             gate.wait(min(n, t + 32u * kFpHalves + 64u + 136u));
-            uint32_t v[kFpHalves], h[kFpHalves], e[kFpHalves], c[kFpHalves], ml[kFpHalves];
-            bool inb[kFpHalves], ok[kFpHalves];
+            // ONE coalesced load per round: lane l holds the aligned word l of the window (20 words cover the 64
+            // positions and the kFpLaneMax bytes behind the last one, whatever the alignment); every position's
+            // twelve bytes (its four, and the two words a match is extended over) are cut out of it with shuffles.
+            const uint32_t bo = t + mis;
+            if (t != w_at) W = fp_window(words, bo, n + mis, lane);
+            // (the next round's window is fetched now: the round after this one starts 64 positions on unless a match
+            //  carries it further -- which, on text, happens in two rounds out of three: a fixed stride that made the
+            //  bet safe, and the next round's table words fetched ahead as well, were both measured and both lost,
+            //  profiles/r2_fastparse.txt)
+            w_at = t + 32u * kFpHalves;
+            const uint32_t Wn = fp_window(words, w_at + mis, n + mis, lane);
+            uint32_t v[kFpHalves], v4[kFpHalves], v8[kFpHalves], h[kFpHalves], e[kFpHalves], c[kFpHalves], ml[kFpHalves];
+            bool inb[kFpHalves], ok[kFpHalves], cap[kFpHalves], cand[kFpHalves];
 #pragma unroll
             for (int k = 0; k < kFpHalves; k++) {
                 const uint32_t p = t + 32u * k + (uint32_t)lane;
+                const uint32_t o = (bo & 3u) + 32u * k + (uint32_t)lane, wi = o >> 2, sh = (o & 3u) * 8u;
+                const uint32_t a0 = __shfl_sync(kFull, W, (int)wi), a1 = __shfl_sync(kFull, W, (int)wi + 1);
+                const uint32_t a2 = __shfl_sync(kFull, W, (int)wi + 2), a3 = __shfl_sync(kFull, W, (int)wi + 3);
+                v[k] = __funnelshift_r(a0, a1, sh); v4[k] = __funnelshift_r(a1, a2, sh); v8[k] = __funnelshift_r(a2, a3, sh);
                 inb[k] = p <= last_start;
-                v[k] = 0; h[k] = 0; e[k] = 0;
-                if (p + 4u <= n) v[k] = S.u32(p);            // (also beyond last_start: the byte is needed as a literal)
+                h[k] = 0; e[k] = 0;
                 if (inb[k]) { h[k] = (v[k] * 2654435761U) >> (32u - kFpTabLog); e[k] = tab[h[k]]; }
             }
             __syncwarp();                                    // every lane has read the old state
@@ -72,79 +98,113 @@ __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, u
                 if (inb[k]) atomicMax(&tab[h[k]], ((p + 1u) << 13) | chk);
                 // the nearest earlier lane of this half with the same four bytes, else the table's candidate
                 const unsigned same = __match_any_sync(kFull, inb[k] ? v[k] : (0x80000000u | (uint32_t)lane) ^ v[k]) & lower;
-                ok[k] = false;
                 c[k] = (e[k] >> 13) - 1u;                    // < t: entries come from earlier rounds
-                if (inb[k] && same) {                        // same four bytes by construction: nothing to verify
-                    c[k] = t + 32u * k + (31u - (uint32_t)__clz(same)); ok[k] = true;
-                } else if (inb[k] && e[k] != 0u && (e[k] & 0x1fffu) == chk && (p - c[k]) <= 65535u) {
-                    ok[k] = S.u32(c[k]) == v[k];
-                }
-                ml[k] = ok[k] ? 4u : 0u;
+                cand[k] = inb[k] && e[k] != 0u && (e[k] & 0x1fffu) == chk && (p - c[k]) <= 65535u;
+                if (inb[k] && same) { c[k] = t + 32u * k + (31u - (uint32_t)__clz(same)); cand[k] = true; }
             }
-            // every lane extends its own matches, word by word, up to kFpLaneMax bytes (both halves in one loop)
-            bool more[kFpHalves];
+            // the candidates' twelve bytes, all halves in flight together (c + 12 < p + 12 <= n: the four words start
+            // inside the unit)
+            uint32_t b[kFpHalves][4];
 #pragma unroll
-            for (int k = 0; k < kFpHalves; k++) more[k] = ok[k];
+            for (int k = 0; k < kFpHalves; k++) {
+                const uint32_t ci = cand[k] ? (c[k] + mis) >> 2 : 0u;
 #pragma unroll
-            for (uint32_t it = 0; it < (kFpLaneMax - 4u) / 4u; it++) {
+                for (int j = 0; j < 4; j++) b[k][j] = words[ci + j];
+            }
 #pragma unroll
-                for (int k = 0; k < kFpHalves; k++) {
-                    const uint32_t p = t + 32u * k + (uint32_t)lane;
-                    more[k] = more[k] && p + ml[k] + 4u <= mlimit;
-                    if (more[k]) {
-                        const uint32_t x = S.u32(p + ml[k]) ^ S.u32(c[k] + ml[k]);
-                        if (x) { ml[k] += (uint32_t)(__ffs(x) - 1) >> 3; more[k] = false; }
-                        else ml[k] += 4u;
+            for (int k = 0; k < kFpHalves; k++) {
+                const uint32_t p = t + 32u * k + (uint32_t)lane;
+                ok[k] = false; ml[k] = 0;
+                if (cand[k]) {
+                    const uint32_t cs = ((c[k] + mis) & 3u) * 8u;
+                    ok[k] = __funnelshift_r(b[k][0], b[k][1], cs) == v[k];
+                    const uint32_t x1 = __funnelshift_r(b[k][1], b[k][2], cs) ^ v4[k], x2 = __funnelshift_r(b[k][2], b[k][3], cs) ^ v8[k];
+                    uint32_t m = 4u;
+                    if (p + 8u <= mlimit) {
+                        if (x1) m = 4u + ((uint32_t)(__ffs(x1) - 1) >> 3);
+                        else if (p + 12u > mlimit) m = 8u;
+                        else m = x2 ? 8u + ((uint32_t)(__ffs(x2) - 1) >> 3) : 12u;
+                    }
+                    if (ok[k]) {
+                        // the last bytes in front of the limit, where no whole word fits (only in a unit's last round)
+                        if (m < kFpLaneMax && p + m + 4u > mlimit) while (p + m < mlimit && src[p + m] == src[c[k] + m]) m++;
+                        ml[k] = m;
                     }
                 }
+                // still equal after kFpLaneMax bytes and room for more: the warp extends it if it is selected
+                cap[k] = ok[k] && ml[k] >= kFpLaneMax && p + ml[k] + 4u <= mlimit;
             }
 #pragma unroll
             for (int k = 0; k < kFpHalves; k++) {
                 const uint32_t tk = t + 32u * k;
                 const uint32_t p = tk + (uint32_t)lane;
-                // ---- greedy selection in position order.  Afterwards: start = I begin a selected sequence (mlen, lit0
-                //      = where its literals begin), seq = the lane whose sequence I am a literal of (32: none)
-                bool start = false;
-                uint32_t mlen = 0, lit0 = 0, seq = 32u;
-                unsigned okm = __ballot_sync(kFull, ok[k]);
-                while (okm) {
-                    const uint32_t arel = anchor > tk ? anchor - tk : 0u;     // first lane of this half that may start a match
-                    if (arel >= 32u) break;
-                    okm &= ~((1u << arel) - 1u);
-                    if (!okm) break;
-                    const int s = __ffs(okm) - 1;
-                    okm &= okm - 1u;
-                    const uint32_t ps = tk + (uint32_t)s;
-                    const uint32_t cs = __shfl_sync(kFull, c[k], s);
-                    uint32_t mls = __shfl_sync(kFull, ml[k], s);
-                    if (mls >= kFpLaneMax && ps + mls + 4u <= mlimit) {
-                        // still equal after kFpLaneMax bytes: the warp extends it, lane j compares the word at +4j, 128 bytes per step
-                        for (;;) {
-                            const uint32_t q = mls + 4u * (uint32_t)lane;
-                            uint32_t eq = 0;                              // equal bytes my word contributes
-                            if (ps + q + 4u <= mlimit) {
-                                const uint32_t x = S.u32(ps + q) ^ S.u32(cs + q);
-                                eq = x ? ((uint32_t)(__ffs(x) - 1) >> 3) : 4u;
-                            } else {
-                                while (eq < 4u && ps + q + eq < mlimit && src[ps + q + eq] == src[cs + q + eq]) eq++;
-                            }
-                            const unsigned part = __ballot_sync(kFull, eq < 4u);
-                            if (part) {
-                                const int j = __ffs(part) - 1;
-                                mls += 4u * (uint32_t)j + __shfl_sync(kFull, eq, j);
-                                break;
-                            }
-                            mls += 128u;
-                        }
-                    } else if (mls < kFpLaneMax && ps + mls + 4u > mlimit) {
-                        while (ps + mls < mlimit && src[ps + mls] == src[cs + mls]) mls++;    // the last bytes before the limit
+                // ---- greedy selection in position order (first match at or after the end of the previous one), done
+                //      for all lanes at once: J = the match that follows mine if mine is selected; three rounds of
+                //      pointer jumping give every match the set M of matches selected from it on (at most eight:
+                //      a match covers four positions or more).  A match the warp still has to extend ends a chain.
+                const unsigned okm = __ballot_sync(kFull, ok[k]);
+                const uint32_t anchor0 = anchor;
+                unsigned sel = 0;
+                uint32_t mlen = ml[k];
+                if (okm) {
+                    const unsigned capm = __ballot_sync(kFull, cap[k]);
+                    const uint32_t er = (uint32_t)lane + ml[k];
+                    const unsigned after = er < 32u ? okm >> er : 0u;
+                    uint32_t J = (ok[k] && !cap[k] && after) ? er + (uint32_t)(__ffs(after) - 1) : 32u;
+                    unsigned M = ok[k] ? 1u << lane : 0u;
+#pragma unroll
+                    for (int it = 0; it < 3; it++) {
+                        const unsigned Mj = __shfl_sync(kFull, M, (int)(J & 31u));
+                        const uint32_t Jj = __shfl_sync(kFull, J, (int)(J & 31u));
+                        if (J < 32u) { M |= Mj; J = Jj; }
                     }
-                    if (lane == s) { start = true; mlen = mls; lit0 = anchor; }
-                    if (p >= anchor && p < ps) seq = (uint32_t)s;
-                    anchor = ps + mls;
+                    for (;;) {
+                        const uint32_t arel = anchor > tk ? anchor - tk : 0u;     // first lane of this half that may start a match
+                        if (arel >= 32u) break;
+                        const unsigned rest = okm >> arel;
+                        if (!rest) break;
+                        const int s = (int)arel + __ffs(rest) - 1;
+                        const unsigned Ms = __shfl_sync(kFull, M, s);
+                        sel |= Ms;
+                        const int z = 31 - __clz(Ms);                              // the chain's last match
+                        uint32_t mls = __shfl_sync(kFull, ml[k], z);
+                        const uint32_t ps = tk + (uint32_t)z;
+                        if ((capm >> z) & 1u) {
+                            // lane j compares the word at +4j, 128 bytes per step
+                            const uint32_t cs = __shfl_sync(kFull, c[k], z);
+                            for (;;) {
+                                const uint32_t q = mls + 4u * (uint32_t)lane;
+                                uint32_t eq = 0;                              // equal bytes my word contributes
+                                if (ps + q + 4u <= mlimit) {
+                                    const uint32_t x = S.u32(ps + q) ^ S.u32(cs + q);
+                                    eq = x ? ((uint32_t)(__ffs(x) - 1) >> 3) : 4u;
+                                } else {
+                                    while (eq < 4u && ps + q + eq < mlimit && src[ps + q + eq] == src[cs + q + eq]) eq++;
+                                }
+                                const unsigned part = __ballot_sync(kFull, eq < 4u);
+                                if (part) {
+                                    const int j = __ffs(part) - 1;
+                                    mls += 4u * (uint32_t)j + __shfl_sync(kFull, eq, j);
+                                    break;
+                                }
+                                mls += 128u;
+                            }
+                            if (lane == z) mlen = mls;
+                            anchor = ps + mls;                                 // ... and the selection goes on behind it
+                        } else {
+                            anchor = ps + mls;                                 // the chain ran out of the half
+                            break;
+                        }
+                    }
                 }
+                // what the emission needs: start = I begin a selected sequence (mlen, lit0 = where its literals begin),
+                // seq = the lane whose sequence I am a literal of (32: none)
+                const bool start = (sel >> lane) & 1u;
+                const unsigned below = sel & lower, above = lane < 31 ? (sel >> (lane + 1)) : 0u;
+                const uint32_t endp = __shfl_sync(kFull, p + mlen, (31 - __clz(below)) & 31);
+                const uint32_t lit0 = below ? endp : anchor0;
+                const uint32_t seq = (!start && above && p >= lit0) ? (uint32_t)lane + (uint32_t)__ffs(above) : 32u;
                 // ---- lane-parallel emission of the half's sequences
-                const unsigned sel = __ballot_sync(kFull, start);
                 if (sel) {
                     const uint32_t ll = p - lit0, code = mlen - 4u;
                     const uint32_t ll_ext = (start && ll >= 15u) ? (ll - 15u) / 255u + 1u : 0u;
@@ -165,16 +225,17 @@ __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, u
                     if (seq < 32u) dst[lb + p] = (uint8_t)v[k];
                     // literals in front of the half (left over by earlier rounds) belong to the first sequence
                     const int s0 = __ffs(sel) - 1;
-                    const uint32_t l0 = __shfl_sync(kFull, lit0, s0), b0 = __shfl_sync(kFull, litbase, s0);
-                    if (l0 < tk) {
-                        const uint32_t pend = tk - l0;
-                        if (pend <= 32u) { if ((uint32_t)lane < pend) dst[b0 + l0 + lane] = src[l0 + lane]; }
-                        else warp_copy(dst + (uint32_t)(b0 + l0), src + l0, pend, lane);   // (b0 is a difference: wrap in 32 bits first)
+                    const uint32_t b0 = __shfl_sync(kFull, litbase, s0);
+                    if (anchor0 < tk) {
+                        const uint32_t pend = tk - anchor0;
+                        if (pend <= 32u) { if ((uint32_t)lane < pend) dst[(uint32_t)(b0 + anchor0 + lane)] = src[anchor0 + lane]; }
+                        else warp_copy(dst + (uint32_t)(b0 + anchor0), src + anchor0, pend, lane);   // (b0 is a difference: wrap in 32 bits first)
                     }
                     op += __shfl_sync(kFull, incl, 31);
                 }
             }
             t = max(t + 32u * kFpHalves, anchor);            // the inside of a match that leaves the round is skipped
+            W = Wn;
         }
     }
     gate.wait(n);

@@ -58,6 +58,9 @@ __device__ __forceinline__ uint32_t snappy_lean_count(const LeanSrc& S, uint32_t
 
 __device__ inline uint32_t snappy_encode_fragment_lean(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst,
                                                        uint16_t* tab, uint32_t* claim, int lane) {
+    // (keeps the fragment's input and output addresses in register pairs: under the register cap of the fragment
+    //  kernels the compiler would rather rebuild them from the kernel parameters in front of an access)
+    asm volatile("" : "+l"(src), "+l"(dst));
     const LeanSrc S(src);
     uint32_t tsize = 256;                                   // snappy.cc:619-632
     if (n > 16384) tsize = 16384; else while (tsize < n) tsize <<= 1;

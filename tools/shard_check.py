@@ -108,6 +108,23 @@ def main():
         for codec in (0, 4):
             want = orc.compress(data, codec) if orc is not None else None
             one_case(name, data, codec, want)
+    # one rank's piece does not fit its buffer: that rank fails, nobody hangs (the neighbours still get the boundary
+    # literals they inherit from it), and the next call on the same communicator works
+    data = rs.integers(0, 256, 6 << 20, dtype=np.uint8)
+    for codec in (0, 4):
+        first, count, boff, blen = llc_b200.shard_range(codec, len(data), rank, world)
+        d_slice = torch.from_numpy(data[boff:boff + blen].copy()).cuda()
+        small = rank == world // 2
+        d_piece = torch.zeros(4096 if small else L.aocl_gpu_compress_bound(codec, len(data)), dtype=torch.uint8, device="cuda")
+        total, off, ln = ctx.compress_sharded(codec, d_slice, len(data), d_piece)
+        torch.cuda.synchronize(); dist.barrier()
+        got = [None] * world
+        dist.all_gather_object(got, int(total))
+        good = all((g < 0) == (r == world // 2) for r, g in enumerate(got))
+        ok_all = ok_all and good
+        if rank == 0:
+            print(json.dumps({"case": "one rank's buffer too small", "codec": codec, "returns": got, "ok": good}), flush=True)
+    one_case("after the failed call", gen.text_like(8 << 20, seed=65), 0, None)
     if args.bench:
         big = bench.make_data("text_like", 1 << 30, 2024)
         for _ in range(3):
