@@ -210,7 +210,7 @@ uint64_t now_ns() {
 // compute stream wait only for the watermark reset.  Returns false if this input takes the plain path.
 bool stream_input_up(HostCtx& h, int codec, const char* in, size_t n, void* d_in, cudaStream_t s) {
     if (n < kPipeMinBytes || !pinned_host(in) || !ensure_pipe(h)) return false;
-    const uint32_t T = (uint32_t)aocl_gpu_partition_count(codec, n);
+    const uint32_t T = (uint32_t)aocl_gpu_ctx_partition_count(h.ctx, codec, n);
     if (T < 2 || (codec == LZ4 && h.lz4_frameless)) return false;
     bool ok = cudaMemsetAsync(h.d_flag, 0, sizeof(uint32_t), h.up) == cudaSuccess &&
               cudaEventRecord(h.ev[0], h.up) == cudaSuccess && cudaStreamWaitEvent(s, h.ev[0], 0) == cudaSuccess;
@@ -375,6 +375,7 @@ int64_t run_codec_sharded(bool compress, int codec, char* in, size_t in_size, ch
         std::lock_guard<std::mutex> lock(g.mu);
         if (g.lz4_frameless) return -100;
     }
+    if (compress) { const char* e = getenv("AOCL_GPU_PARTITIONS"); if (e && atoi(e) > 0) return -100; }   // an imitated host layout is not sharded
     std::lock_guard<std::mutex> lock(sg.mu);
     if (!shard_group_init()) return -100;
     const int R = (int)sg.rank.size();

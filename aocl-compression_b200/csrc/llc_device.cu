@@ -62,6 +62,7 @@ struct aocl_gpu_ctx_s {
     uint32_t rowq_min_units = 0;    // AOCL_GPU_ROWQ_MIN_UNITS: auto mode takes the row decoder from this many units on
     bool lz4_frameless = false;
     bool fastparse = false;         // AOCL_GPU_MODE=fastparse / aocl_gpu_set_mode(): the named non-exact LZ4 RAP encoder
+    uint32_t max_parts = 0;         // AOCL_GPU_PARTITIONS / aocl_gpu_set_partitions(): the host's omp_get_max_threads() to imitate (0: none)
     const uint32_t* in_flag = nullptr;   // one-shot input watermark for the next compress (aocl_gpu_set_input_watermark)
     bool batch_mode = false;        // last enqueue was a batch call (finish() returns -failures)
     int last_rc = 0;                // enqueue-time failure to report from finish()
@@ -129,6 +130,7 @@ extern "C" int32_t aocl_gpu_ctx_create(aocl_gpu_ctx_t* out, int device, void* st
         if (getenv("AOCL_GPU_VERBOSE")) fprintf(stderr, "[aocl-llc-b200] L2 persisting max %d B, window max %d B\n", max_persist, max_window);
     }
     if (const char* e = getenv("AOCL_GPU_MODE")) c->fastparse = strcmp(e, "fastparse") == 0;
+    if (const char* e = getenv("AOCL_GPU_PARTITIONS")) c->max_parts = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("AOCL_GPU_GTAB_CTAS")) c->gtab_ctas_per_sm = atoi(e);
     if (const char* e = getenv("AOCL_GPU_SNAPPY_GTAB_CTAS")) c->snappy_gtab_ctas_per_sm = atoi(e);
     if (const char* e = getenv("AOCL_GPU_SNAPPY_STAB_CTAS")) c->snappy_stab_ctas_per_sm = atoi(e);
@@ -183,6 +185,21 @@ extern "C" int32_t aocl_gpu_set_mode(aocl_gpu_ctx_t c, const char* mode) {
     if (strcmp(mode, "exact") == 0) { c->fastparse = false; return 0; }
     if (strcmp(mode, "fastparse") == 0) { c->fastparse = true; return 0; }
     return -4;
+}
+// threads/threads.c:55-88: the frame has min(omp_get_max_threads(), P(n)) partitions
+static uint32_t frame_parts(aocl_gpu_ctx_t c, size_t n, uint32_t window) {
+    const uint32_t T = partition_count(n, window);
+    return (c->max_parts && T > c->max_parts) ? c->max_parts : T;
+}
+extern "C" int32_t aocl_gpu_set_partitions(aocl_gpu_ctx_t c, int32_t max_threads) {
+    if (!c || max_threads < 0) return -5;
+    c->max_parts = (uint32_t)max_threads;
+    return 0;
+}
+extern "C" int32_t aocl_gpu_ctx_partition_count(aocl_gpu_ctx_t c, int32_t codec, size_t n) {
+    if (!c) return -5;
+    if (codec == AOCL_GPU_LZ4 && c->lz4_frameless) return 1;
+    return (int32_t)frame_parts(c, n, codec == AOCL_GPU_LZ4 ? kLz4Window : kSnappyBlock);
 }
 extern "C" void aocl_gpu_set_input_watermark(aocl_gpu_ctx_t c, const uint32_t* d_flag) { if (c) c->in_flag = d_flag; }
 extern "C" uint64_t aocl_gpu_launch_count(void) { return g_launches.load(); }
@@ -349,7 +366,7 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
     const uint8_t* src = (const uint8_t*)d_in;
     uint8_t* dst = (uint8_t*)d_out;
     if (codec == AOCL_GPU_LZ4) {
-        const uint32_t T = c->lz4_frameless ? 1u : partition_count(n, kLz4Window);
+        const uint32_t T = c->lz4_frameless ? 1u : frame_parts(c, n, kLz4Window);
         if (T == 1) {                                          // frame-less block, lz4.c:2674-2677 / 2485-2541
             const uint64_t bound = n + n / 255 + 16;
             LLC_LAUNCH(lz4_encode_single_kernel, 1, 32, 16384, c->stream, src, (uint32_t)n, dst,
@@ -358,7 +375,9 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
             const uint64_t pmax = n / T + n % T;
             const uint64_t slot = align_up(pmax + pmax / 255 + 32, 256);
             int stab = c->stab_ctas_per_sm, gtab = c->gtab_ctas_per_sm;
-            if (c->fastparse) { stab = 0; if (gtab <= 0) gtab = 32; }      // one flavour: tables in L2, every partition resident
+            // (fastparse packs positions in 19 bits: the larger partitions of an imitated host layout take the exact encoder)
+            const bool fastparse = c->fastparse && pmax < (1u << 19);
+            if (fastparse) { stab = 0; if (gtab <= 0) gtab = 32; }      // one flavour: tables in L2, every partition resident
             if (stab < 0 && gtab < 0) {                        // auto: one wave if at all possible
                 if (T <= (uint32_t)c->sm_count * (uint32_t)kStabMax) { stab = kStabMax; gtab = 0; } else { stab = 0; gtab = 32; }
             }
@@ -378,7 +397,7 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
             cudaMemsetAsync(ticket, 0, sizeof(uint32_t), c->stream);
             const uint32_t a_cap = (uint32_t)c->sm_count * (uint32_t)stab;
             const int a_grid = (int)(T < a_cap ? T : a_cap);
-            const int enc_slot = prof_begin(c, c->fastparse ? "lz4_fastparse_parts_kernel" : "lz4_encode_parts_kernel");   // brackets both flavours (fork .. join)
+            const int enc_slot = prof_begin(c, fastparse ? "lz4_fastparse_parts_kernel" : "lz4_encode_parts_kernel");   // brackets both flavours (fork .. join)
             if (g_ctas > 0 && T > (uint32_t)a_grid) {
                 // fork: the global-table flavour shares the ticket and fills the idle warp slots
                 cudaEventRecord(c->ev_fork, c->stream);
@@ -394,7 +413,7 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
                     av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
                     cudaStreamSetAttribute(c->side, cudaStreamAttributeAccessPolicyWindow, &av);
                 }
-                if (c->fastparse)
+                if (fastparse)
                     lz4_fastparse_parts_kernel<<<(int)(T < (uint32_t)g_ctas ? T : (uint32_t)g_ctas), 32, 0, c->side>>>(
                         src, Lz4Range{(uint64_t)n, T, 0u, T}, scratch, slot, rec, ticket, tables, in_flag, c->d_res);
                 else
@@ -415,7 +434,7 @@ extern "C" int32_t aocl_gpu_compress_async(aocl_gpu_ctx_t c, int32_t codec, cons
         }
     } else {
         if (out_cap < 32 + n + n / 6) { c->last_rc = -2; return -2; }   // api/codec.cpp:262-265
-        const uint32_t T = partition_count(n, kSnappyBlock);
+        const uint32_t T = frame_parts(c, n, kSnappyBlock);
         const SnappyGeom g = snappy_geom(n, T);
         const uint32_t F = g.frags_total;
         const uint64_t slot = 76544;                           // >= 32 + 65536 + 65536/6, multiple of 256

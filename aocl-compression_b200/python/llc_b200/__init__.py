@@ -68,7 +68,8 @@ GPU_API = ["aocl_gpu_ctx_create", "aocl_gpu_ctx_destroy", "aocl_gpu_ctx_stream",
            "aocl_gpu_debug_counters", "aocl_gpu_set_input_watermark", "aocl_gpu_decompress_open_async",
            "aocl_gpu_decompress_slab_async", "aocl_gpu_decompress_close_async",
            "aocl_gpu_shard_unique_id", "aocl_gpu_shard_init", "aocl_gpu_shard_destroy", "aocl_gpu_shard_range",
-           "aocl_gpu_compress_sharded", "aocl_gpu_decompress_sharded", "aocl_gpu_set_mode", "aocl_gpu_sharded_host_calls"]
+           "aocl_gpu_compress_sharded", "aocl_gpu_decompress_sharded", "aocl_gpu_set_mode", "aocl_gpu_sharded_host_calls",
+           "aocl_gpu_set_partitions", "aocl_gpu_ctx_partition_count"]
 
 _lib = None
 
@@ -115,6 +116,7 @@ def load() -> C.CDLL:
         "aocl_gpu_decompress_slab_async": (i32, [vp, i32, vp, vp, u32, u32]),
         "aocl_gpu_decompress_close_async": (i32, [vp]),
         "aocl_gpu_set_mode": (i32, [vp, C.c_char_p]),
+        "aocl_gpu_set_partitions": (i32, [vp, i32]), "aocl_gpu_ctx_partition_count": (i32, [vp, i32, sz]),
         "aocl_gpu_sharded_host_calls": (u64, []),
         "aocl_gpu_shard_unique_id": (i32, [vp]),
         "aocl_gpu_shard_init": (i32, [vp, vp, i32, i32]),
@@ -188,6 +190,13 @@ class GpuContext:
     def set_mode(self, mode: str) -> int:
         """"exact" (default) or "fastparse" (the named non-exact LZ4 RAP encoder)."""
         return self.L.aocl_gpu_set_mode(self.h, mode.encode())
+
+    def set_partitions(self, max_threads: int) -> int:
+        """Write the frames of a host with `max_threads` OpenMP threads (0: the saturated layout, default)."""
+        return self.L.aocl_gpu_set_partitions(self.h, max_threads)
+
+    def partition_count(self, codec, n) -> int:
+        return self.L.aocl_gpu_ctx_partition_count(self.h, codec, n)
 
     def set_profiling(self, on: bool):
         self.L.aocl_gpu_set_profiling(self.h, 1 if on else 0)

@@ -73,11 +73,24 @@ void aocl_gpu_set_lz4_frameless(aocl_gpu_ctx_t ctx, int32_t on);
  * Returns 0, -4 for an unknown mode. */
 int32_t aocl_gpu_set_mode(aocl_gpu_ctx_t ctx, const char *mode);
 
+/* Partition layout of the frames this context writes (env AOCL_GPU_PARTITIONS at context creation, or this call).
+ * The reference cuts a frame into min(omp_get_max_threads(), P(n)) partitions (threads/threads.c:55-88), so what a host
+ * emits depends on its thread count.  The default (0) is the saturated layout T = P(n) -- what a host with at least P(n)
+ * threads writes, and the only layout with GPU-sized parallelism.  max_threads = K makes this context write, byte for
+ * byte, the frame of a K-thread host: K partitions of n/K bytes.  LZ4 partitions are serial chains, one warp each: a
+ * K-partition frame compresses at K x ~7 MB/s -- this is for byte comparison and interop, not for speed.  Snappy is
+ * not affected in speed (its unit of work is the 64 KiB fragment whatever the layout).  fastparse falls back to the
+ * exact encoder for partitions of 512 KiB and more.  The sharded calls always use the saturated layout.
+ * Decompression reads every layout regardless.  Returns 0, -5 for a bad argument. */
+int32_t aocl_gpu_set_partitions(aocl_gpu_ctx_t ctx, int32_t max_threads);
+/* Partitions a frame of n bytes written by THIS context will have (aocl_gpu_partition_count: the saturated P(n)). */
+int32_t aocl_gpu_ctx_partition_count(aocl_gpu_ctx_t ctx, int32_t codec, size_t n);
+
 /* Streaming input for the NEXT aocl_gpu_compress_async on this context (one-shot).  d_flag points to a
  * 32-bit watermark in device memory that the caller raises (e.g. with 4-byte H2D copies ordered after
  * the payload copies on its own copy stream) while the encoder is already running:
  *   LZ4 RAP frames:  bytes present in EVERY partition (send the input in stripes across partitions:
- *                    partition i occupies [i*(n/T), (i+1)*(n/T)), T = aocl_gpu_partition_count);
+ *                    partition i occupies [i*(n/T), (i+1)*(n/T)), T = aocl_gpu_ctx_partition_count);
  *   Snappy:          bytes present from the start of the input.
  * Raise it to 0xffffffff once everything (including the last partition's n % T extra bytes) is there.
  * Encoder warps wait on the watermark before they touch input beyond it (with a 64-byte margin, so a

@@ -66,6 +66,74 @@ def test_gpu_decodes_reference_streams_of_unsaturated_hosts(gpu_lib, ref, codec)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("codec", [kat.LZ4, kat.SNAPPY])
+def test_gpu_writes_the_frames_of_unsaturated_hosts(oracle, ref, codec):
+    """aocl_gpu_set_partitions(K) / AOCL_GPU_PARTITIONS=K: the GPU writes, byte for byte, the frame a host with K OpenMP
+    threads writes -- min(K, P(n)) partitions of n / T bytes (threads/threads.c:55-88); checked against the oracle at
+    that thread count and against the compiled reference itself."""
+    import torch
+    import llc_b200
+    n = (6 << 20) + 12345
+    data = _interop_input(n)
+    L = llc_b200.load()
+    ctx = llc_b200.GpuContext(0)
+    try:
+        d_in = torch.from_numpy(data).cuda()
+        d_comp = torch.zeros(L.aocl_gpu_compress_bound(codec, n), dtype=torch.uint8, device="cuda")
+        d_back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        P = oracle.partition_count(n, codec)
+        for K in (1, 2, 3, 5, 8, 16, P + 7):
+            want = oracle.compress(data, codec, max_threads=K)
+            assert ctx.set_partitions(K) == 0
+            assert ctx.partition_count(codec, n) == min(K, P) == oracle.partition_count(n, codec, K)
+            got = ctx.compress(codec, d_in, d_comp)
+            assert got == len(want) and d_comp[:got].cpu().numpy().tobytes() == want, (codec, K)
+            assert ctx.decompress(codec, d_comp, got, d_back) == n and torch.equal(d_back, d_in), (codec, K)
+            if ref is not None and K <= 16:
+                ref.set_threads(K)
+                r, stream = ref.compress(data, codec)
+                assert r == len(want) and stream == want, (codec, K, "the oracle's layout is not the reference's")
+        assert ctx.set_partitions(0) == 0 and ctx.set_partitions(-1) == -5
+        got = ctx.compress(codec, d_in, d_comp)
+        assert d_comp[:got].cpu().numpy().tobytes() == oracle.compress(data, codec)
+    finally:
+        if ref is not None:
+            ref.set_threads(os.cpu_count() or 8)
+        ctx.close()
+
+
+_HOST_LAYOUT = r"""
+import sys
+import numpy as np, torch
+sys.path[:0] = ["tests", "aocl-compression_b200/python"]
+import llc_b200, oracle_lib as ol
+lib = ol.LlcLib(llc_b200.LIB_PATH)
+orc = ol.Oracle()
+from llc_b200 import gen
+n = (40 << 20) + 777                                   # above the pipelined-transfer threshold
+data = np.concatenate([gen.log_like(n // 2, seed=5), gen.mixed_entropy(n - n // 2)])
+pin = torch.from_numpy(data).pin_memory().numpy()      # pinned: the striped, watermarked H2D path
+for codec in (ol.LZ4, ol.SNAPPY):
+    want = orc.compress(data, codec, max_threads=3)
+    r, stream = lib.compress(pin, codec)
+    assert r == len(want) and stream == want, (codec, r, len(want))
+    assert int.from_bytes(stream[12:16], "little") == 3
+    r2, back = lib.decompress(stream, codec, n)
+    assert r2 == n and back == data.tobytes()
+print("HOST LAYOUT OK")
+"""
+
+
+@pytest.mark.gpu
+def test_host_api_follows_aocl_gpu_partitions():
+    """AOCL_GPU_PARTITIONS=3 in the environment: aocl_llc_compress (pinned input, transfers pipelined behind the
+    watermark with the 3-partition stripe geometry) writes the 3-thread host's frame."""
+    env = dict(os.environ, AOCL_GPU_PARTITIONS="3")
+    r = subprocess.run([sys.executable, "-c", _HOST_LAYOUT], env=env, capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0 and "HOST LAYOUT OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.gpu
 def test_gpu_decodes_lz4hc_streams(gpu_lib, ref):
     """setup(LZ4HC) succeeds, decompress(LZ4HC) is the LZ4 decoder, compress(LZ4HC) is refused."""
     import ctypes as C
