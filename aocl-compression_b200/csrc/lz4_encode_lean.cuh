@@ -137,15 +137,15 @@ __device__ __forceinline__ LeanProbe lean_verify_issue(const LeanSrc& S, uint32_
     LeanProbe v;
     v.pa = mpos + 4u * (uint32_t)lane - 4u;
     if (mpos >= 4u && mcand >= 4u) {
-        // The 32 lanes read 128 contiguous bytes of each stream: one aligned word per lane, the following
-        // word comes from the next lane.  Lane 31 has no next lane; it does not take part (see finish).
+        // The 32 lanes read 128 contiguous bytes of each stream: one aligned word per lane; the following word
+        // comes from the next lane, in lean_verify_finish -- a shuffle here would be the loads' first use and put
+        // their whole latency in front of the emission that is meant to run in its shadow (20 % of all stall
+        // samples sat on these two shuffles).  Lane 31 has no next lane; it does not take part.
         const uint32_t qa = S.so + mpos - 4u, qb = S.so + mcand - 4u;
         const uint32_t ia = (qa >> 2) + (uint32_t)lane, ib = (qb >> 2) + (uint32_t)lane;
         const uint32_t last = (S.so + n - 1u) >> 2;         // last aligned word that holds bytes of the unit
-        const uint32_t wa = ia <= last ? S.w[ia] : 0u, wb = ib <= last ? S.w[ib] : 0u;
-        const uint32_t wa1 = __shfl_down_sync(kFull, wa, 1), wb1 = __shfl_down_sync(kFull, wb, 1);
-        v.xa = __funnelshift_r(wa, wa1, (qa & 3u) * 8u);
-        v.xb = __funnelshift_r(wb, wb1, (qb & 3u) * 8u);
+        v.xa = ia <= last ? S.w[ia] : 0u;
+        v.xb = ib <= last ? S.w[ib] : 0u;
         v.look = lane == 0 ? from_search : (lane == 1 || (lane < 31 && v.pa < mlimit));
     } else {                                                // within 4 bytes of the start of the unit: per-lane loads
         v.look = lane == 0 ? false : (lane == 1 || (lane < 31 && v.pa < mlimit));
@@ -158,9 +158,15 @@ __device__ __forceinline__ LeanProbe lean_verify_issue(const LeanSrc& S, uint32_
 // eqb = equal bytes among the four before the two positions.
 __device__ __forceinline__ bool lean_verify_finish(const LeanSrc& S, const LeanProbe& v, uint32_t mpos, uint32_t mcand,
                                                    uint32_t mlimit, uint32_t n, int lane, InGate& gate, uint32_t& mc, uint32_t& eqb) {
+    uint32_t xa = v.xa, xb = v.xb;
+    if (mpos >= 4u && mcand >= 4u) {                        // (uniform) aligned words -> the four bytes at this lane's offset
+        const uint32_t wa1 = __shfl_down_sync(kFull, xa, 1), wb1 = __shfl_down_sync(kFull, xb, 1);
+        xa = __funnelshift_r(xa, wa1, ((S.so + mpos - 4u) & 3u) * 8u);
+        xb = __funnelshift_r(xb, wb1, ((S.so + mcand - 4u) & 3u) * 8u);
+    }
     uint32_t c = 0;                                         // equal bytes in this lane's word
     if (v.look) {
-        const uint32_t x = v.xa ^ v.xb;
+        const uint32_t x = xa ^ xb;
         c = (uint32_t)__clz(lane == 0 ? x : __brev(x)) >> 3;             // from the top for lane 0, from the bottom otherwise
         if (lane >= 2) c = min(c, mlimit - v.pa);
     }

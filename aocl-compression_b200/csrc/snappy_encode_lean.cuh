@@ -35,16 +35,26 @@ __device__ __forceinline__ void snappy_lean_emit(const SnappyPending& q, const u
     op = snappy_put_copy(dst, op, q.off, q.len, lane);                                                         // snappy.cc:1004
 }
 
-// bytes equal from p / p - delta on, bounded by n (FindMatchLength, snappy-internal.h:228-352)
-__device__ __forceinline__ uint32_t snappy_lean_count(const LeanSrc& S, uint32_t p, uint32_t delta, uint32_t n, int lane) {
-    uint32_t total = 0;
+// bytes equal from p / p - delta on, bounded by n (FindMatchLength, snappy-internal.h:228-352): the 32 lanes read 128
+// contiguous bytes of each stream, one aligned word per lane (the next word comes from the next lane), 124 bytes per
+// round trip.  Split in two so that the pending emission runs between the first loads and their first use.
+struct SnappyCount { uint32_t wa, wb; };
+__device__ __forceinline__ SnappyCount snappy_lean_count_issue(const LeanSrc& S, uint32_t p, uint32_t delta, uint32_t n, int lane) {
     const uint32_t last = (S.so + n - 1u) >> 2;             // last aligned word that holds bytes of the fragment
+    const uint32_t qa = S.so + p, qb = qa - delta;
+    const uint32_t ia = (qa >> 2) + (uint32_t)lane, ib = (qb >> 2) + (uint32_t)lane;
+    SnappyCount c;
+    c.wa = ia <= last ? S.w[ia] : 0u;
+    c.wb = ib <= last ? S.w[ib] : 0u;
+    return c;
+}
+__device__ __forceinline__ uint32_t snappy_lean_count_finish(const LeanSrc& S, SnappyCount ld, uint32_t p, uint32_t delta, uint32_t n,
+                                                             int lane) {
+    uint32_t total = 0;
     for (;;) {
         const uint32_t qa = S.so + p, qb = qa - delta;
-        const uint32_t ia = (qa >> 2) + (uint32_t)lane, ib = (qb >> 2) + (uint32_t)lane;
-        const uint32_t wa = ia <= last ? S.w[ia] : 0u, wb = ib <= last ? S.w[ib] : 0u;
-        const uint32_t wa1 = __shfl_down_sync(kFull, wa, 1), wb1 = __shfl_down_sync(kFull, wb, 1);
-        const uint32_t x = __funnelshift_r(wa, wa1, (qa & 3u) * 8u) ^ __funnelshift_r(wb, wb1, (qb & 3u) * 8u);
+        const uint32_t wa1 = __shfl_down_sync(kFull, ld.wa, 1), wb1 = __shfl_down_sync(kFull, ld.wb, 1);
+        const uint32_t x = __funnelshift_r(ld.wa, wa1, (qa & 3u) * 8u) ^ __funnelshift_r(ld.wb, wb1, (qb & 3u) * 8u);
         const uint32_t pa = p + 4u * (uint32_t)lane;
         uint32_t c = 0;                                     // lane 31 has no next word: it only ends the round
         if (lane < 31 && pa < n) c = min((uint32_t)__clz(__brev(x)) >> 3, n - pa);
@@ -53,6 +63,7 @@ __device__ __forceinline__ uint32_t snappy_lean_count(const LeanSrc& S, uint32_t
         total += 4u * (uint32_t)first + __shfl_sync(kFull, c, first);
         if (first < 31) return total;
         p += 124u;
+        ld = snappy_lean_count_issue(S, p, delta, n, lane);
     }
 }
 
@@ -147,8 +158,9 @@ __device__ inline uint32_t snappy_encode_fragment_lean(const uint8_t* __restrict
                 wmask |= upto_win;
                 const uint32_t mpos = __shfl_sync(kFull, cur, win);
                 const uint32_t mcand = __shfl_sync(kFull, cand, win);
-                const uint32_t len = 4u + snappy_lean_count(S, mpos + 4u, mpos - mcand, n, lane);   // snappy.cc:995-1003
-                if (pend.valid) snappy_lean_emit(pend, src, dst, op, lane);
+                const SnappyCount ld = snappy_lean_count_issue(S, mpos + 4u, mpos - mcand, n, lane);
+                if (pend.valid) snappy_lean_emit(pend, src, dst, op, lane);          // ... in the shadow of those loads
+                const uint32_t len = 4u + snappy_lean_count_finish(S, ld, mpos + 4u, mpos - mcand, n, lane);   // snappy.cc:995-1003
                 pend.valid = true; pend.lit_from = anchor; pend.mpos = mpos; pend.off = mpos - mcand; pend.len = len;
                 const uint32_t nbase = mpos + len;
                 anchor = nbase;
