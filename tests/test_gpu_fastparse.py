@@ -56,3 +56,30 @@ def test_fastparse_streams_decode_everywhere(oracle, ref):
         assert ctx.set_mode("exact") == 0 and ctx.set_mode("nonsense") == -4
     finally:
         ctx.close()
+
+
+def test_fastparse_with_an_imitated_host_layout(oracle):
+    """fastparse packs positions in 19 bits.  With aocl_gpu_set_partitions() the partitions can be larger than that:
+    those frames take the exact encoder (and are then the K-thread host's bytes); smaller ones stay fastparse."""
+    import torch
+    import llc_b200
+    from llc_b200 import gen
+    data = gen.text_like(3 << 20, seed=75)
+    n = len(data)
+    ctx = llc_b200.GpuContext(0)
+    try:
+        d_in = torch.from_numpy(data).cuda()
+        d_comp = torch.zeros(ctx.L.aocl_gpu_compress_bound(kat.LZ4, n), dtype=torch.uint8, device="cuda")
+        d_back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        assert ctx.set_mode("fastparse") == 0
+        assert ctx.set_partitions(2) == 0                                     # 1.5 MiB partitions: exact encoder
+        c = ctx.compress(kat.LZ4, d_in, d_comp)
+        assert c > 0 and d_comp[:c].cpu().numpy().tobytes() == oracle.compress(data, kat.LZ4, max_threads=2)
+        assert ctx.set_partitions(8) == 0                                     # 384 KiB partitions: fastparse
+        c8 = ctx.compress(kat.LZ4, d_in, d_comp)
+        stream = d_comp[:c8].cpu().numpy().tobytes()
+        assert c8 > 0 and int.from_bytes(stream[12:16], "little") == 8 and stream != oracle.compress(data, kat.LZ4, max_threads=8)
+        assert oracle.decompress(stream, kat.LZ4, n) == data.tobytes()
+        assert ctx.decompress(kat.LZ4, d_comp, c8, d_back) == n and torch.equal(d_back, d_in)
+    finally:
+        ctx.close()
