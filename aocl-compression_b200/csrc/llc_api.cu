@@ -266,6 +266,7 @@ int64_t decompress_pipelined(HostCtx& h, int codec, const char* in, size_t n, ch
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h.device);
     uint32_t per = sms > 0 ? 2u * (uint32_t)sms : 256u;
+    if (const char* e = getenv("AOCL_GPU_SLAB_PARTS")) { const int v = atoi(e); if (v >= 64) per = (uint32_t)v; }   // tuning knob
     while ((T + per - 1) / per > 24) per += sms > 0 ? 2u * (uint32_t)sms : 256u;
     const int K = (int)((T + per - 1) / per);
     if (K < 2) return -100;
