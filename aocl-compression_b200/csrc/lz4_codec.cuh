@@ -101,159 +101,9 @@ __device__ __forceinline__ void lz4_put_ext(uint8_t* dst, uint32_t v, int lane) 
     for (uint32_t j = lane; j < count; j += 32) dst[j] = (j + 1 < count) ? (uint8_t)255 : (uint8_t)(v % 255);
 }
 
-template <bool WIDE>
-__device__ inline uint32_t lz4_encode_warp_impl(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, int64_t cap,
-                                                bool emit_tail, uint32_t* tail_len, uint32_t* tab_mem, int lane, InGate& gate) {
-    Lz4Table<WIDE> tab{tab_mem};
-    gate.wait(n);                                           // this variant does not stream its input
-    for (int i = lane; i < 4096; i += 32) tab_mem[i] = 0;   // zeroed table: slot value 0 == position 0
-    __syncwarp();
-
-    const bool limited = cap >= 0;
-    uint32_t op = 0, anchor = 0;
-    bool refused = false;
-
-    if (n >= 13) {                                          // LZ4_minLength, lz4.c:1926
-        const uint32_t mfl1 = n - 11;                       // mflimitPlusOne, lz4.c:1887
-        const uint32_t mlimit = n - 5;                      // matchlimit, lz4.c:1888
-        tab.put(tab.hash(src), 0);                          // lz4.c:1929
-        __syncwarp();
-        uint32_t ip = 1;
-        for (;;) {
-            // ---------------- search: 32 speculative probes per round ----------------
-            uint32_t fwd = ip, step = 1, nb = 64, m = 0;
-            bool found = false;
-            for (;;) {
-                const uint32_t my_step = (lane == 0) ? step : ((nb + lane - 1) >> 6);
-                const uint32_t incl = warp_incl_sum(my_step, lane);
-                const uint32_t cur = fwd + incl - my_step;
-                const uint32_t nxt = fwd + incl;
-                const bool valid = nxt <= mfl1;                          // lz4.c:2001
-                uint32_t h = 0x80000000u | lane, seq4 = 0, cand = 0;
-                if (valid) {
-                    if (WIDE) { uint64_t v = ld_u64(src + cur); seq4 = (uint32_t)v; h = lz4_hash5(v); }
-                    else      { seq4 = ld_u32(src + cur); h = lz4_hash4(seq4); }
-                    cand = tab.get(h);
-                }
-                const unsigned peers = __match_any_sync(kFull, h);
-                const unsigned before = peers & ((1u << lane) - 1u);
-                const int from = before ? (31 - __clz(before)) : lane;
-                const uint32_t peer_pos = __shfl_sync(kFull, cur, from);
-                if (before) cand = peer_pos;
-                bool hit = false;
-                if (valid) hit = (ld_u32(src + cand) == seq4) && (!WIDE || cur - cand <= 65535u);
-                const unsigned events = __ballot_sync(kFull, hit || !valid);
-                const int win = events ? (__ffs(events) - 1) : 32;
-                const bool win_is_match = (win < 32) && ((__ballot_sync(kFull, hit) >> win) & 1u);
-                // commit table writes for probes the serial algorithm would have executed
-                const unsigned commit = (win_is_match ? (win == 31 ? kFull : ((2u << win) - 1u))
-                                                      : (win == 0 ? 0u : (win >= 32 ? kFull : ((1u << win) - 1u))));
-                if (valid && ((commit >> lane) & 1u)) {
-                    const unsigned mine = peers & commit;
-                    if ((31 - __clz(mine)) == lane) tab.put(h, cur);
-                }
-                __syncwarp();
-                if (win < 32) {
-                    if (win_is_match) {
-                        ip = __shfl_sync(kFull, cur, win);
-                        m = __shfl_sync(kFull, cand, win);
-                        found = true;
-                    }
-                    break;
-                }
-                fwd = __shfl_sync(kFull, nxt, 31);
-                step = (nb + 31) >> 6;
-                nb += 32;
-            }
-            if (!found) break;                              // -> closing literals
-
-            // ---------------- catch up backwards, lz4.c:2098 ----------------
-            for (;;) {
-                const bool can = (ip > anchor + lane) && (m > (uint32_t)lane);
-                const bool eq = can && (src[ip - 1 - lane] == src[m - 1 - lane]);
-                const unsigned ne = __ballot_sync(kFull, !eq);
-                const uint32_t cnt = ne ? (uint32_t)(__ffs(ne) - 1) : 32u;
-                ip -= cnt; m -= cnt;
-                if (cnt < 32) break;
-            }
-
-            uint32_t ll = ip - anchor;
-            bool from_search = true;
-            for (;;) {                                      // _next_match, lz4.c:2126-2288
-                // match length: lanes compare 4 bytes each, 128 bytes per round (LZ4_count, lz4.c:656-679)
-                uint32_t mc = 0;
-                {
-                    const uint32_t delta = ip - m;
-                    uint32_t base = ip + 4;
-                    for (;;) {
-                        const uint32_t pa = base + 4u * lane;
-                        uint32_t c = 0;
-                        if (pa < mlimit) {
-                            const uint32_t avail = min(4u, mlimit - pa);
-                            const uint32_t x = ld_u32(src + pa) ^ ld_u32(src + pa - delta);
-                            c = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
-                            c = min(c, avail);
-                        }
-                        const unsigned partial = __ballot_sync(kFull, c < 4);
-                        if (partial) {
-                            const int first = __ffs(partial) - 1;
-                            mc += 4u * first + __shfl_sync(kFull, c, first);
-                            break;
-                        }
-                        mc += 128; base += 128;
-                    }
-                }
-                // ---- emit: token | literal-length bytes | literals | offset | match-length bytes
-                const uint32_t ll_ext = ll >= 15 ? (ll - 15) / 255 + 1 : 0;
-                const uint32_t ml_ext = mc >= 15 ? (mc - 15) / 255 + 1 : 0;
-                if (limited) {
-                    // lz4.c:2104-2107 (literals) and lz4.c:2177-2204 (match length)
-                    if (from_search && (int64_t)op + 1 + ll + 8 + ll / 255 > cap) { refused = true; break; }
-                    if ((int64_t)op + 1 + ll_ext + ll + 2 + 6 + (mc + 240) / 255 > cap) { refused = true; break; }
-                }
-                if (lane == 0) dst[op] = (uint8_t)((min(ll, 15u) << 4) | min(mc, 15u));
-                if (ll_ext) lz4_put_ext(dst + op + 1, ll - 15, lane);
-                warp_copy(dst + op + 1 + ll_ext, src + anchor, ll, lane);
-                op += 1 + ll_ext + ll;
-                if (lane == 0) { dst[op] = (uint8_t)(ip - m); dst[op + 1] = (uint8_t)((ip - m) >> 8); }
-                op += 2;
-                if (ml_ext) lz4_put_ext(dst + op, mc - 15, lane);
-                op += ml_ext;
-
-                ip += mc + 4;
-                anchor = ip;
-                ll = 0;
-                from_search = false;
-                if (ip >= mfl1) break;                      // lz4.c:2227
-                // every lane performs the same table updates, so program order is enough
-                tab.put(tab.hash(src + ip - 2), ip - 2);    // lz4.c:2230
-                const uint32_t h = tab.hash(src + ip);
-                m = tab.get(h);
-                tab.put(h, ip);
-                if ((!WIDE || m + 65535u >= ip) && ld_u32(src + m) == ld_u32(src + ip)) continue;   // lz4.c:2278-2286
-                m = 0xffffffffu;
-                break;
-            }
-            __syncwarp();
-            if (refused || ip >= mfl1) break;
-            ip++;                                           // lz4.c:2291
-        }
-    }
-    if (refused) return 0;
-    const uint32_t run = n - anchor;
-    if (!emit_tail) { if (tail_len) *tail_len = run; return op; }        // lz4.c:2333-2338
-    if (tail_len) *tail_len = 0;
-    if (limited && (int64_t)op + run + 1 + (run + 255 - 15) / 255 > cap) return 0;   // lz4.c:2299-2311
-    const uint32_t ext = run >= 15 ? (run - 15) / 255 + 1 : 0;
-    if (lane == 0) dst[op] = (uint8_t)(min(run, 15u) << 4);
-    if (ext) lz4_put_ext(dst + op + 1, run - 15, lane);
-    warp_copy(dst + op + 1 + ext, src + anchor, run, lane);
-    return op + 1 + ext + run;
-}
-
 // -------------------------------------------------------------------------------------------
-// Encoder, fused-round version.  Same parse as lz4_encode_warp_impl, reorganised so that one
-// sequence costs two dependent global round trips instead of six:
+// Encoder, fused-round version (units below 65,547 bytes -- the byU16 / hash4 table -- and frame-less blocks of
+// 512 KiB and more; RAP partitions take lz4_encode_lean.cuh).  One sequence costs two dependent global round trips:
 //   * every lane loads a 12-byte window [p-4, p+8) around its probe position and, after the table
 //     lookup, around its candidate; from the two windows it derives locally whether the candidate
 //     verifies, how far the match extends backwards (catch-up, up to 4 bytes) and forwards (up to 8
@@ -460,13 +310,8 @@ __device__ inline uint32_t lz4_encode_warp_fused(const uint8_t* __restrict__ src
 __device__ inline uint32_t lz4_encode_warp(const uint8_t* src, uint32_t n, uint8_t* dst, int64_t cap, bool emit_tail,
                                            uint32_t* tail_len, uint32_t* tab_mem, int lane, InGate& gate) {
     if (n == 0) { if (lane == 0) dst[0] = 0; if (tail_len) *tail_len = 0; return 1; }   // lz4.c:2418-2428
-#ifdef LLC_LZ4_ENCODER_SIMPLE
-    if (n >= 65547) return lz4_encode_warp_impl<true>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane, gate);
-    return lz4_encode_warp_impl<false>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane, gate);
-#else
     if (n >= 65547) return lz4_encode_warp_fused<true>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane, gate);
     return lz4_encode_warp_fused<false>(src, n, dst, cap, emit_tail, tail_len, tab_mem, lane, gate);
-#endif
 }
 
 }  // namespace llc

@@ -115,120 +115,5 @@ __device__ __forceinline__ uint32_t snappy_put_copy(uint8_t* dst, uint32_t op, u
     return op + 3;
 }
 
-// Encode one fragment (n <= 65536) with a u16 hash table of `tsize` entries in shared memory.
-// Same speculative 32-probe search as the LZ4 encoder; the probe schedule is
-// stride = skip >> 5, skip += stride, starting at skip = 32 (snappy.cc:903-974; the reference's
-// unrolled 16-probe prologue is the same walk).
-__device__ inline uint32_t snappy_encode_fragment_warp(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst,
-                                                       uint16_t* tab, int lane) {
-    uint32_t tsize = 256;                                   // snappy.cc:619-632
-    if (n > 16384) tsize = 16384; else while (tsize < n) tsize <<= 1;
-    const int shift = 32 - (31 - __clz(tsize));
-    for (uint32_t i = lane; i < tsize / 2; i += 32) reinterpret_cast<uint32_t*>(tab)[i] = 0;
-    __syncwarp();
-    uint32_t op = 0, ip = 0;
-    if (n >= 15) {
-        const uint32_t ip_limit = n - 15;
-        bool done = false;
-        while (!done) {
-            const uint32_t next_emit = ip++;
-            uint32_t skip = 32, cand = 0;
-            bool found = false;
-            for (;;) {
-                // stride of the j-th upcoming probe: the skip counter grows by its own stride, so the
-                // per-lane value is produced by a short serial recurrence on lane 0's state
-                uint32_t my_stride, s = skip;
-                if (skip <= 32) {
-                    s = skip + lane;                        // first round of a search: stride 1 throughout
-                    my_stride = 1;
-                } else {
-                    // lanes need skip_k = skip after k probes; each lane replays the recurrence
-                    // (at most 31 cheap steps; only reached after 32 fruitless probes)
-                    for (int k = 0; k < lane; k++) s += s >> 5;
-                    my_stride = s >> 5;
-                }
-                const uint32_t incl = warp_incl_sum(my_stride, lane);
-                const uint32_t cur = ip + incl - my_stride;
-                const uint32_t nxt = ip + incl;
-                const bool valid = nxt <= ip_limit;
-                uint32_t h = 0x80000000u | lane, seq4 = 0, c = 0;
-                if (valid) {
-                    seq4 = ld_u32(src + cur);
-                    h = (seq4 * 0x1e35a7bdU) >> shift;      // snappy.cc:152-158
-                    c = tab[h];
-                }
-                const unsigned peers = __match_any_sync(kFull, h);
-                const unsigned before = peers & ((1u << lane) - 1u);
-                const int from = before ? (31 - __clz(before)) : lane;
-                const uint32_t peer_pos = __shfl_sync(kFull, cur, from);
-                if (before) c = peer_pos;
-                bool hit = false;
-                if (valid) hit = ld_u32(src + c) == seq4;
-                const unsigned hits = __ballot_sync(kFull, hit);
-                const unsigned events = hits | __ballot_sync(kFull, !valid);
-                const int win = events ? (__ffs(events) - 1) : 32;
-                const bool win_is_match = (win < 32) && ((hits >> win) & 1u);
-                const unsigned commit = (win_is_match ? (win == 31 ? kFull : ((2u << win) - 1u))
-                                                      : (win == 0 ? 0u : (win >= 32 ? kFull : ((1u << win) - 1u))));
-                if (valid && ((commit >> lane) & 1u)) {
-                    const unsigned mine = peers & commit;
-                    if ((31 - __clz(mine)) == lane) tab[h] = (uint16_t)cur;
-                }
-                __syncwarp();
-                if (win < 32) {
-                    if (win_is_match) { ip = __shfl_sync(kFull, cur, win); cand = __shfl_sync(kFull, c, win); found = true; }
-                    break;
-                }
-                ip = __shfl_sync(kFull, nxt, 31);
-                skip = __shfl_sync(kFull, s + (s >> 5), 31);
-            }
-            if (!found) { ip = next_emit; break; }          // -> emit_remainder
-            op = snappy_put_literal(dst, op, src + next_emit, ip - next_emit, lane);   // snappy.cc:980
-            for (;;) {                                      // snappy.cc:995-1032
-                // match length: 4 + common prefix, bounded by the fragment end
-                uint32_t mc = 0;
-                {
-                    const uint32_t delta = ip - cand;
-                    uint32_t base = ip + 4;
-                    for (;;) {
-                        const uint32_t pa = base + 4u * lane;
-                        uint32_t cc = 0;
-                        if (pa < n) {
-                            const uint32_t avail = min(4u, n - pa);
-                            uint32_t x;
-                            if (avail == 4) x = ld_u32(src + pa) ^ ld_u32(src + pa - delta);
-                            else {
-                                x = 0;
-                                for (uint32_t b = 0; b < avail; b++) x |= (uint32_t)(src[pa + b] ^ src[pa - delta + b]) << (8 * b);
-                            }
-                            cc = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
-                            cc = min(cc, avail);
-                        }
-                        const unsigned partial = __ballot_sync(kFull, cc < 4);
-                        if (partial) {
-                            const int first = __ffs(partial) - 1;
-                            mc += 4u * first + __shfl_sync(kFull, cc, first);
-                            break;
-                        }
-                        mc += 128; base += 128;
-                    }
-                }
-                const uint32_t len = 4 + mc;
-                op = snappy_put_copy(dst, op, ip - cand, len, lane);
-                ip += len;
-                if (ip >= ip_limit) { done = true; break; }
-                const uint32_t prev4 = ld_u32(src + ip - 1), cur4 = ld_u32(src + ip);
-                tab[(prev4 * 0x1e35a7bdU) >> shift] = (uint16_t)(ip - 1);   // snappy.cc:1016-1021
-                const uint32_t h = (cur4 * 0x1e35a7bdU) >> shift;
-                cand = tab[h];
-                tab[h] = (uint16_t)ip;
-                if (ld_u32(src + cand) != cur4) break;
-            }
-            __syncwarp();
-        }
-    }
-    if (ip < n) op = snappy_put_literal(dst, op, src + ip, n - ip, lane);   // snappy.cc:1039-1043
-    return op;
-}
 
 }  // namespace llc

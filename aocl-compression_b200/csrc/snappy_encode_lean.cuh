@@ -1,8 +1,10 @@
 // snappy_encode_lean.cuh -- the Snappy fragment encoder the RAP path runs.
 //
-// Same exact parse as snappy_encode_fragment_warp (snappy_codec.cuh), which follows the reference's
-// AOCL_CompressFragment (algos/snappy/snappy.cc:846-1046; emitters :436-568) bit for bit, reorganised the
-// way the LZ4 partition encoder was (lz4_encode_lean.cuh) after its ncu captures:
+// Follows the reference's AOCL_CompressFragment (algos/snappy/snappy.cc:846-1046; emitters :436-568) bit for
+// bit: one warp evaluates the next 32 probe slots of the serial schedule at once (stride = skip >> 5,
+// skip += stride, starting at skip = 32: snappy.cc:903-974; the reference's unrolled 16-probe prologue is the
+// same walk) and commits the table writes of the slots the serial algorithm would have executed.  Organised
+// the way the LZ4 partition encoder is (lz4_encode_lean.cuh), after its ncu captures:
 //   * the "insert ip-1, probe ip" that follows a copy (snappy.cc:1016-1032) is lanes 0 and 1 of the next
 //     round, in front of the first 30 probes of the next search (stride 1: skip runs 32..61), so every
 //     lane runs the same code;
