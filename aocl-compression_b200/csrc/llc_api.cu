@@ -267,13 +267,16 @@ int64_t decompress_pipelined(HostCtx& h, int codec, const char* in, size_t n, ch
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h.device);
     uint32_t per = sms > 0 ? 2u * (uint32_t)sms : 256u;
     if (const char* e = getenv("AOCL_GPU_SLAB_PARTS")) { const int v = atoi(e); if (v >= 64) per = (uint32_t)v; }   // tuning knob
-    while ((T + per - 1) / per > 24) per += sms > 0 ? 2u * (uint32_t)sms : 256u;
-    const int K = (int)((T + per - 1) / per);
+    while ((T + per - 1) / per > 23) per += sms > 0 ? 2u * (uint32_t)sms : 256u;
+    // the first slab is a quarter wave: the download link, which is what the call takes, starts that much earlier
+    const uint32_t head = T >= 4u * per ? per / 4u : 0u;
+    const int K = (int)((T - head + per - 1) / per) + (head ? 1 : 0);
     if (K < 2) return -100;
     uint64_t in_end[24], out_end[24];
     uint32_t first[25];
     uint64_t pos = frame, total = 0;
-    for (int k = 0; k < K; k++) first[k] = (uint32_t)k * per;
+    first[0] = 0;
+    for (int k = 1; k < K; k++) first[k] = head ? head + (uint32_t)(k - 1) * per : (uint32_t)k * per;
     first[K] = T;
     for (int k = 0; k < K; k++) {
         for (uint32_t i = first[k]; i < first[k + 1]; i++) {
