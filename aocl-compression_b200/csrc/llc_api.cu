@@ -208,16 +208,25 @@ uint64_t now_ns() {
 // Enqueue the H2D transfer of a pinned host input on the copy stream in pieces, each followed by a
 // 4-byte copy that raises the encoder's input watermark (include/aocl_llc_gpu.h), and make the
 // compute stream wait only for the watermark reset.  Returns false if this input takes the plain path.
+// `in` / `n`: the bytes of this call's piece of the frame -- the whole input, or one GPU's partition range when the call is
+// split over several GPUs: then T and common are the partitions of that range and the frame's bytes per partition, and
+// mark_base the piece's offset in the frame (Snappy's watermark counts bytes of the frame).
+bool stream_piece_up(HostCtx& h, int codec, const char* in, size_t n, void* d_in, cudaStream_t s, uint32_t T, size_t common,
+                     uint64_t mark_base);
 bool stream_input_up(HostCtx& h, int codec, const char* in, size_t n, void* d_in, cudaStream_t s) {
-    if (n < kPipeMinBytes || !pinned_host(in) || !ensure_pipe(h)) return false;
     const uint32_t T = (uint32_t)aocl_gpu_ctx_partition_count(h.ctx, codec, n);
     if (T < 2 || (codec == LZ4 && h.lz4_frameless)) return false;
+    return stream_piece_up(h, codec, in, n, d_in, s, T, n / T, 0);
+}
+bool stream_piece_up(HostCtx& h, int codec, const char* in, size_t n, void* d_in, cudaStream_t s, uint32_t T, size_t common,
+                     uint64_t mark_base) {
+    if (n < kPipeMinBytes || !pinned_host(in) || !ensure_pipe(h)) return false;
     bool ok = cudaMemsetAsync(h.d_flag, 0, sizeof(uint32_t), h.up) == cudaSuccess &&
               cudaEventRecord(h.ev[0], h.up) == cudaSuccess && cudaStreamWaitEvent(s, h.ev[0], 0) == cudaSuccess;
     int pieces = 0;
     if (codec == LZ4) {
         // stripe j = bytes [j*w, (j+1)*w) of EVERY partition (a 2-D copy, pitch = partition size)
-        const size_t common = n / T, w = 16384;
+        const size_t w = 16384;
         pieces = (int)(common / w);
         if (pieces < 1) pieces = 1;
         if (pieces > kMaxPieces) pieces = kMaxPieces;
@@ -235,7 +244,7 @@ bool stream_input_up(HostCtx& h, int codec, const char* in, size_t n, void* d_in
         for (int j = 0; j < pieces && ok; j++) {
             const size_t lo = (size_t)j * piece, len = (j == pieces - 1) ? n - lo : piece;
             ok = cudaMemcpyAsync((char*)d_in + lo, in + lo, len, cudaMemcpyHostToDevice, h.up) == cudaSuccess;
-            h.h_marks[j] = (j == pieces - 1) ? 0xffffffffu : (uint32_t)(lo + len);
+            h.h_marks[j] = (j == pieces - 1) ? 0xffffffffu : (uint32_t)(mark_base + lo + len);
             ok = ok && cudaMemcpyAsync(h.d_flag, &h.h_marks[j], sizeof(uint32_t), cudaMemcpyHostToDevice, h.up) == cudaSuccess;
         }
     }
@@ -385,6 +394,7 @@ int64_t run_codec_sharded(bool compress, int codec, char* in, size_t in_size, ch
     const int R = (int)sg.rank.size();
     uint32_t T = 0;
     std::vector<uint64_t> in_lo(R), in_hi(R), out_need(R);
+    std::vector<uint32_t> parts(R, 0);
     uint64_t head_bytes = 0;                                  // decompress: frame header (+ varint) every rank needs
     if (compress) {
         T = (uint32_t)aocl_gpu_partition_count(codec, in_size);
@@ -392,7 +402,7 @@ int64_t run_codec_sharded(bool compress, int codec, char* in, size_t in_size, ch
         for (int r = 0; r < R; r++) {
             uint32_t first, count; uint64_t off, len;
             if (aocl_gpu_shard_range(codec, in_size, r, R, &first, &count, &off, &len) != 0) return -100;
-            in_lo[r] = off; in_hi[r] = off + len;
+            in_lo[r] = off; in_hi[r] = off + len; parts[r] = count;
             out_need[r] = aocl_gpu_compress_bound(codec, len) + 16 + 12 * (uint64_t)T + 64;
         }
     } else {
@@ -443,8 +453,12 @@ int64_t run_codec_sharded(bool compress, int codec, char* in, size_t in_size, ch
             uint64_t off = 0, len = 0;
             int64_t tot;
             if (compress) {
-                cudaMemcpyAsync(h.d_in, in + in_lo[r], in_hi[r] - in_lo[r], cudaMemcpyHostToDevice, s);
+                // the slice goes up in stripes behind the encoder's watermark, as in the single-GPU call
+                const bool streamed = stream_piece_up(h, codec, in + in_lo[r], (size_t)(in_hi[r] - in_lo[r]), h.d_in, s, parts[r],
+                                                      (size_t)(in_size / T), in_lo[r]);
+                if (!streamed) cudaMemcpyAsync(h.d_in, in + in_lo[r], in_hi[r] - in_lo[r], cudaMemcpyHostToDevice, s);
                 tot = aocl_gpu_compress_sharded(h.ctx, codec, h.d_in, in_size, h.d_out, out_need[r], &off, &len);
+                if (streamed) { cudaStreamSynchronize(h.up); aocl_gpu_set_input_watermark(h.ctx, nullptr); }
                 if (tot > 0 && off + len <= out_size && cudaMemcpyAsync(out + off, h.d_out, len, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
                     cudaStreamSynchronize(s) == cudaSuccess) result[r] = tot;
                 else if (tot > 0) result[r] = -1;

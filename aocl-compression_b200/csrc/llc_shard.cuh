@@ -145,6 +145,8 @@ extern "C" int64_t aocl_gpu_compress_sharded(aocl_gpu_ctx_t c, int32_t codec, co
     uint64_t my_off = 0, my_len = 0;
     if (!d_in_slice || !d_out_slice || n > 0x7E000000ull || aocl_gpu_shard_range(codec, n, me, R, &p0, &cnt, &my_off, &my_len) != 0) return -2;
     begin_call(c);
+    const uint32_t* in_flag = c->in_flag;                     // one-shot (aocl_gpu_set_input_watermark): the slice is still arriving
+    c->in_flag = nullptr;
     const uint8_t* src = (const uint8_t*)d_in_slice;
     uint8_t* dst = (uint8_t*)d_out_slice;
     cudaStream_t st = c->stream;
@@ -168,8 +170,8 @@ extern "C" int64_t aocl_gpu_compress_sharded(aocl_gpu_ctx_t c, int32_t codec, co
         uint8_t* scratch = c->ws + o_scr;
         cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
         const Lz4Range g{(uint64_t)n, T, p0, cnt};
-        if (stab) LLC_LAUNCH(lz4_encode_parts_kernel, grid, 32, 16384, st, src, g, scratch, slot, rec, ticket, (const uint32_t*)nullptr, c->d_res);
-        else LLC_LAUNCH(lz4_encode_parts_gtab_kernel, grid, 32, 0, st, src, g, scratch, slot, rec, ticket, tables, (const uint32_t*)nullptr, c->d_res);
+        if (stab) LLC_LAUNCH(lz4_encode_parts_kernel, grid, 32, 16384, st, src, g, scratch, slot, rec, ticket, in_flag, c->d_res);
+        else LLC_LAUNCH(lz4_encode_parts_gtab_kernel, grid, 32, 0, st, src, g, scratch, slot, rec, ticket, tables, in_flag, c->d_res);
         // all-gather (in place, ranges differ by at most one partition) of the partition records
         ok = shard_ok(a.GroupStart(), "GroupStart");
         for (int r = 0; r < R && ok; r++) {
@@ -242,8 +244,8 @@ extern "C" int64_t aocl_gpu_compress_sharded(aocl_gpu_ctx_t c, int32_t codec, co
         uint16_t* tables = reinterpret_cast<uint16_t*>(c->ws + o_tab);
         uint8_t* scratch = c->ws + o_scr;
         cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
-        if (stab) LLC_LAUNCH(snappy_encode_frags_kernel, grid, 32, 32768, st, src, g, scratch, slot, frag_len, ticket, (const uint32_t*)nullptr, c->d_res);
-        else LLC_LAUNCH(snappy_encode_frags_gtab_kernel, grid, 32, 0, st, src, g, scratch, slot, frag_len, ticket, tables, (const uint32_t*)nullptr, c->d_res);
+        if (stab) LLC_LAUNCH(snappy_encode_frags_kernel, grid, 32, 32768, st, src, g, scratch, slot, frag_len, ticket, in_flag, c->d_res);
+        else LLC_LAUNCH(snappy_encode_frags_gtab_kernel, grid, 32, 0, st, src, g, scratch, slot, frag_len, ticket, tables, in_flag, c->d_res);
         ok = shard_ok(a.GroupStart(), "GroupStart");
         for (int r = 0; r < R && ok; r++) {
             const uint32_t lo = shard::part_lo(T, r, R) * g.frags_common;

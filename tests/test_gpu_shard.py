@@ -54,6 +54,7 @@ def test_one_frame_on_two_gpus_matches_the_oracle():
 _HOST_SPLIT = r"""
 import ctypes as C, os, sys
 import numpy as np
+import torch          # (before the library opens libnccl.so.2: torch must find its own, newer NCCL first)
 sys.path.insert(0, os.path.join(ROOT, "aocl-compression_b200", "python")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import llc_b200, oracle_lib as ol
 from llc_b200 import gen
@@ -70,9 +71,16 @@ for name, data in cases.items():
         r2, back = lib.decompress(got, codec, len(data))
         assert r2 == len(data) and back == data.tobytes(), (name, codec, r2)
         print("ok", name, codec, r)
+# pinned buffers: every GPU's slice goes up in stripes behind its encoder's watermark
+data = cases["text+random"]
+pin = torch.from_numpy(data).pin_memory().numpy()
+for codec in (0, 4):
+    r, got = lib.compress(pin, codec)
+    assert r > 0 and got == orc.compress(data, codec), ("pinned", codec, r)
+    print("ok pinned", codec, r)
 L = C.CDLL(llc_b200.LIB_PATH)
 L.aocl_gpu_sharded_host_calls.restype = C.c_uint64
-assert L.aocl_gpu_sharded_host_calls() == 8, L.aocl_gpu_sharded_host_calls()      # 2 inputs x 2 codecs x (compress + decompress)
+assert L.aocl_gpu_sharded_host_calls() == 10, L.aocl_gpu_sharded_host_calls()     # 2 inputs x 2 codecs x (compress + decompress) + 2 pinned
 print("HOST SPLIT OK", L.aocl_gpu_sharded_host_calls())
 """
 
