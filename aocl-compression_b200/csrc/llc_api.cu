@@ -260,7 +260,10 @@ bool stream_piece_up(HostCtx& h, int codec, const char* in, size_t n, void* d_in
 // Host-to-host decompress of a well-formed multi-partition RAP stream in slabs.  Returns bytes
 // produced, -1 on failure, or -100 when the stream does not qualify (caller takes the plain path,
 // which also produces the reference's error behaviour for malformed frames).
-int64_t decompress_pipelined(HostCtx& h, int codec, const char* in, size_t n, char* out, size_t out_size, cudaStream_t s) {
+// With [p_lo, p_hi) a sub-range of the partitions (one GPU's share of a call that is split over several GPUs) only
+// that range is transferred and decoded; the return value is still the whole stream's size.
+int64_t decompress_pipelined(HostCtx& h, int codec, const char* in, size_t n, char* out, size_t out_size, cudaStream_t s,
+                             uint32_t p_lo = 0, uint32_t p_hi = 0xffffffffu) {
     const unsigned char* u = (const unsigned char*)in;
     uint64_t magic = 0;
     if (n < kPipeMinBytes || n > 0xffffffffull) return -100;
@@ -269,6 +272,10 @@ int64_t decompress_pipelined(HostCtx& h, int codec, const char* in, size_t n, ch
     const uint32_t frame = rd32(u + 8), T = rd32(u + 12);
     if (T < 64 || T > 65536 || frame != 16 + 12 * (uint64_t)T || frame > n) return -100;
     if (!pinned_host(in) || !pinned_host(out) || !ensure_pipe(h)) return -100;
+    const bool ranged = p_lo != 0 || p_hi < T;
+    if (p_hi > T) p_hi = T;
+    if (p_lo >= p_hi) return -100;
+    const uint32_t cnt = p_hi - p_lo;
     // A slab is one wave of the tile decoder (one partition per resident CTA, two CTAs per SM), so the
     // slab decodes cost what the single launch costs; at most 24 slabs.  Entries must be laid out back
     // to back in order.
@@ -276,49 +283,57 @@ int64_t decompress_pipelined(HostCtx& h, int codec, const char* in, size_t n, ch
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h.device);
     uint32_t per = sms > 0 ? 2u * (uint32_t)sms : 256u;
     if (const char* e = getenv("AOCL_GPU_SLAB_PARTS")) { const int v = atoi(e); if (v >= 64) per = (uint32_t)v; }   // tuning knob
-    while ((T + per - 1) / per > 23) per += sms > 0 ? 2u * (uint32_t)sms : 256u;
+    while ((cnt + per - 1) / per > 23) per += sms > 0 ? 2u * (uint32_t)sms : 256u;
     // the first slab is a quarter wave: the download link, which is what the call takes, starts that much earlier
-    const uint32_t head = T >= 4u * per ? per / 4u : 0u;
-    const int K = (int)((T - head + per - 1) / per) + (head ? 1 : 0);
-    if (K < 2) return -100;
+    const uint32_t head = cnt >= 4u * per ? per / 4u : 0u;
+    const int K = (int)((cnt - head + per - 1) / per) + (head ? 1 : 0);
+    if (K < 2 && !ranged) return -100;
     uint64_t in_end[24], out_end[24];
     uint32_t first[25];
-    uint64_t pos = frame, total = 0;
-    first[0] = 0;
-    for (int k = 1; k < K; k++) first[k] = head ? head + (uint32_t)(k - 1) * per : (uint32_t)k * per;
-    first[K] = T;
-    for (int k = 0; k < K; k++) {
-        for (uint32_t i = first[k]; i < first[k + 1]; i++) {
-            const unsigned char* e = u + 16 + 12 * (size_t)i;
-            const uint64_t off = rd32(e), clen = rd32(e + 4), dlen = rd32(e + 8);
-            if (off < pos || off + clen > n) return -100;
-            pos = off + clen;
-            if (clen) total += dlen;
-        }
-        in_end[k] = (k == K - 1) ? n : pos;
-        out_end[k] = total;
+    first[0] = p_lo;
+    for (int k = 1; k < K; k++) first[k] = p_lo + (head ? head + (uint32_t)(k - 1) * per : (uint32_t)k * per);
+    first[K] = p_hi;
+    // every entry is checked (each GPU of a split call checks the whole table), the slabs cover the range
+    uint64_t pos = frame, total = 0, in_lo = 0, out_lo = 0, first_off = 0;
+    bool seen_first = false;
+    int k = 0;
+    for (uint32_t i = 0; i < T; i++) {
+        if (i == p_lo) { in_lo = pos; out_lo = total; }
+        const unsigned char* e = u + 16 + 12 * (size_t)i;
+        const uint64_t off = rd32(e), clen = rd32(e + 4), dlen = rd32(e + 8);
+        if (off < pos || off + clen > n) return -100;
+        if (clen && !seen_first) { first_off = off; seen_first = true; }
+        pos = off + clen;
+        if (clen) total += dlen;
+        if (i >= p_lo && i < p_hi && i + 1 == first[k + 1]) { in_end[k] = (i + 1 == T) ? n : pos; out_end[k] = total; k++; }
     }
-    if (total > out_size || total == 0) return -100;
-    if (!grow(h, &h.d_in, &h.d_in_bytes, n) || !grow(h, &h.d_out, &h.d_out_bytes, total)) return -1;
+    if (total > out_size || total == 0 || !seen_first) return -100;
+    if (in_lo < first_off) in_lo = first_off;                // (the frame, and Snappy's varint behind it, travel with the head)
+    const uint64_t out_hi = out_end[K - 1];
+    if (!grow(h, &h.d_in, &h.d_in_bytes, n) || !grow(h, &h.d_out, &h.d_out_bytes, out_hi > out_lo ? out_hi - out_lo : 1)) return -1;
 
-    bool ok = true;
-    uint64_t lo = 0;
-    for (int k = 0; k < K && ok; k++) {                     // all uploads, in order, on the copy stream
-        ok = cudaMemcpyAsync((char*)h.d_in + lo, in + lo, in_end[k] - lo, cudaMemcpyHostToDevice, h.up) == cudaSuccess &&
-             cudaEventRecord(h.ev[1 + k], h.up) == cudaSuccess;
-        lo = in_end[k];
+    // uploads, in order, on the copy stream: the head of the stream (frame, entry table, varint), then the slabs
+    bool ok = cudaMemcpyAsync(h.d_in, in, first_off, cudaMemcpyHostToDevice, h.up) == cudaSuccess &&
+              cudaEventRecord(h.ev[0], h.up) == cudaSuccess;
+    uint64_t lo = in_lo;
+    for (int j = 0; j < K && ok; j++) {
+        if (in_end[j] > lo) ok = cudaMemcpyAsync((char*)h.d_in + lo, in + lo, in_end[j] - lo, cudaMemcpyHostToDevice, h.up) == cudaSuccess;
+        ok = ok && cudaEventRecord(h.ev[1 + j], h.up) == cudaSuccess;
+        if (in_end[j] > lo) lo = in_end[j];
     }
-    ok = ok && cudaStreamWaitEvent(s, h.ev[1], 0) == cudaSuccess &&
+    ok = ok && cudaStreamWaitEvent(s, h.ev[0], 0) == cudaSuccess &&
          aocl_gpu_decompress_open_async(h.ctx, codec, h.d_in, n, out_size) == 0;
-    uint64_t olo = 0;
-    for (int k = 0; k < K && ok; k++) {
-        ok = cudaStreamWaitEvent(s, h.ev[1 + k], 0) == cudaSuccess &&
-             aocl_gpu_decompress_slab_async(h.ctx, codec, h.d_in, h.d_out, first[k], first[k + 1] - first[k]) == 0 &&
-             cudaEventRecord(h.ev[1 + kMaxPieces + k], s) == cudaSuccess &&
-             cudaStreamWaitEvent(h.down, h.ev[1 + kMaxPieces + k], 0) == cudaSuccess;
-        if (ok && out_end[k] > olo)
-            ok = cudaMemcpyAsync(out + olo, (char*)h.d_out + olo, out_end[k] - olo, cudaMemcpyDeviceToHost, h.down) == cudaSuccess;
-        olo = out_end[k];
+    // partitions are decoded to their offsets in the stream's output: the staging buffer stands for [out_lo, out_hi) of it
+    char* const d_base = reinterpret_cast<char*>(reinterpret_cast<uintptr_t>(h.d_out) - (uintptr_t)out_lo);
+    uint64_t olo = out_lo;
+    for (int j = 0; j < K && ok; j++) {
+        ok = cudaStreamWaitEvent(s, h.ev[1 + j], 0) == cudaSuccess &&
+             aocl_gpu_decompress_slab_async(h.ctx, codec, h.d_in, d_base, first[j], first[j + 1] - first[j]) == 0 &&
+             cudaEventRecord(h.ev[1 + kMaxPieces + j], s) == cudaSuccess &&
+             cudaStreamWaitEvent(h.down, h.ev[1 + kMaxPieces + j], 0) == cudaSuccess;
+        if (ok && out_end[j] > olo)
+            ok = cudaMemcpyAsync(out + olo, d_base + olo, out_end[j] - olo, cudaMemcpyDeviceToHost, h.down) == cudaSuccess;
+        if (out_end[j] > olo) olo = out_end[j];
     }
     if (ok) ok = aocl_gpu_decompress_close_async(h.ctx) == 0;
     const int64_t r = ok ? aocl_gpu_finish(h.ctx) : -1;
@@ -434,6 +449,7 @@ int64_t run_codec_sharded(bool compress, int codec, char* in, size_t in_size, ch
         }
         if (total > out_size) return -1;
     }
+    const bool pipe_decode = !compress && T >= 64 && in_size >= kPipeMinBytes && pinned_host(in) && pinned_host(out);
     std::vector<int64_t> result(R, -1);
     std::vector<uint64_t> piece_off(R, 0), piece_len(R, 0);
     std::atomic<int> alloc_bad{0}, arrived{0};
@@ -462,6 +478,13 @@ int64_t run_codec_sharded(bool compress, int codec, char* in, size_t in_size, ch
                 if (tot > 0 && off + len <= out_size && cudaMemcpyAsync(out + off, h.d_out, len, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
                     cudaStreamSynchronize(s) == cudaSuccess) result[r] = tot;
                 else if (tot > 0) result[r] = -1;
+            } else if (pipe_decode) {
+                // pinned buffers: every GPU runs the slab pipeline (upload | decode | download) on its partition range;
+                // the ranks are threads of this process, so they agree on the outcome here and need no collective
+                result[r] = decompress_pipelined(h, codec, in, in_size, out, out_size, s, (uint32_t)((uint64_t)T * r / R),
+                                                 (uint32_t)((uint64_t)T * (r + 1) / R));
+                cudaGetLastError();
+                return;
             } else {
                 cudaMemcpyAsync(h.d_in, in, head_bytes, cudaMemcpyHostToDevice, s);
                 if (in_hi[r] > in_lo[r]) cudaMemcpyAsync((char*)h.d_in + in_lo[r], in + in_lo[r], in_hi[r] - in_lo[r], cudaMemcpyHostToDevice, s);
@@ -474,6 +497,7 @@ int64_t run_codec_sharded(bool compress, int codec, char* in, size_t in_size, ch
         });
     for (auto& t : th) t.join();
     if (alloc_bad.load()) return -1;
+    if (pipe_decode) for (int r = 0; r < R; r++) if (result[r] == -100) return -100;     // does not qualify after all: the single-GPU path decides
     for (int r = 0; r < R; r++) if (result[r] < 0 || result[r] != result[0]) return -1;
     g_sharded_calls++;
     return result[0];
