@@ -274,10 +274,10 @@ __device__ inline uint32_t lz4_encode_warp_lean(const uint8_t* __restrict__ src,
             const uint32_t lit = lo & 0xffu;
 
             // ---------------- sequences of this round ----------------
-            // A post round whose 32 slots hit 32 different buckets (no clash) keeps going after a match: the
-            // slots behind the match are the insert / probe / search slots of the NEXT sequence, their table
-            // entries are already here and cannot have been touched by the slots committed so far.  So one
-            // gather serves every sequence that starts inside the 32-position window (2-3 for text).
+            // A post round keeps going after a match: the slots behind the match are the insert / probe / search
+            // slots of the NEXT sequence, and their table entries are already here -- untouched by the slots
+            // committed so far unless two slots share a bucket, in which case the candidates are worked out again
+            // (below).  So one gather serves every sequence that starts inside the 32-position window (2-3 for text).
             unsigned wmask = post ? 1u : 0u;                // slots whose table write is committed (lane 0: insert of base-2)
             int s_lane = post ? 1 : 0;                      // slot of the current sequence's first probe
             bool next_post = false;
@@ -318,9 +318,20 @@ __device__ inline uint32_t lz4_encode_warp_lean(const uint8_t* __restrict__ src,
                 anchor = nbase;
                 if (nbase >= mfl1) { finished = true; break; }          // lz4.c:2227
                 const uint32_t nl = nbase - base + 1u;      // slot of nbase in this round's layout
-                if (!post || clashed || nl > 31u) { base = nbase; next_post = true; break; }
+                if (!post || nl > 31u) { base = nbase; next_post = true; break; }
                 wmask |= 1u << (nl - 2u);                   // insert of nbase-2 (lz4.c:2230)
                 s_lane = (int)nl;
+                if (clashed) {
+                    // Slots that share a bucket: a slot's candidate is the nearest earlier slot of its bucket that the
+                    // serial algorithm EXECUTES, else the table entry.  The slots inside the match were not executed, so
+                    // the slots behind it look again -- among the committed slots (wmask) and the slots from nbase on.
+                    const unsigned live = (wmask | ~((1u << s_lane) - 1u)) & peers & ((1u << lane) - 1u);
+                    const int f = live ? (31 - __clz(live)) : lane;
+                    const uint32_t ppos = __shfl_sync(kFull, cur, f), pchk = __shfl_sync(kFull, chk, f);
+                    cand = live ? ppos : (entry & kLeanPosMask);
+                    cchk = live ? pchk : (entry >> 19);
+                    mb = __ballot_sync(kFull, valid && probe && cchk == chk && cur - cand <= 65535u);
+                }
             }
 
             // ---------------- commit the table writes the serial algorithm would have made ----------------
