@@ -8,10 +8,12 @@
 //   * every lane hashes its own positions and reads the table (the state BEFORE this round), then all lanes insert
 //     with atomicMax -- the table ends up holding the highest position per bucket whatever the order of the lanes,
 //     so the output is deterministic; repeats closer than a round are found with MATCH.ANY on the four bytes;
-//   * every lane verifies its candidate (4 equal bytes, distance <= 65535) and extends its own match, word by
-//     word, up to 36 bytes; longer matches are extended by the whole warp, 128 bytes per step, only if selected;
-//   * the greedy selection walks the round's matches in position order (first match at or after the end of the
-//     previous one); literals, token and offset of each selected sequence are written by the warp.
+//   * the round's bytes come from one coalesced load of 20 aligned words, cut to size with shuffles; every lane
+//     fetches its candidate's twelve bytes in one go, verifies it (4 equal bytes, distance <= 65535) and knows its
+//     match length up to 12; longer matches are extended by the whole warp, 128 bytes per step, only if selected;
+//   * the greedy selection (first match at or after the end of the previous one) is worked out for all lanes at
+//     once by pointer jumping over "the match that follows mine"; literals, token and offset of the selected
+//     sequences are written lane parallel.
 // Deviations from the reference's parse that cost ratio (reported by bench.py as `ratio_delta_vs_exact`): matches
 // against positions of the same round only inside one 32-position half, no backward catch-up
 // (lz4.c:2098), every position of a round is inserted (the reference skips the inside of matches and accelerates
@@ -43,8 +45,8 @@ __device__ __forceinline__ uint32_t fp_window(const uint32_t* words, uint32_t by
 // match extension) overlap.  All halves read the table as it was BEFORE the round and insert afterwards; a repeat
 // closer than that is found inside a half with MATCH.ANY on the four bytes (the nearest earlier lane with the same
 // bytes), which is what catches runs and the short periods of columnar data.
-// Per half: the greedy selection walks the matches in position order (uniform loop, a few instructions per
-// sequence: every lane learns whether it is a match start, a literal of which sequence, or covered); then the
+// Per half: the greedy selection by pointer jumping (every lane learns whether it is a match start, a literal of
+// which sequence, or covered; the warp only loops over matches it has to extend); then the
 // sequences of the half are written LANE PARALLEL -- a warp scan of their sizes gives every sequence its place, the
 // start lanes write token / length bytes / offset, every literal lane writes its own byte.
 __device__ inline uint32_t lz4_fastparse_unit(const uint8_t* __restrict__ src, uint32_t n, uint8_t* dst, bool emit_tail,
